@@ -1,0 +1,165 @@
+/*
+ * libsfsim_atmosphere.so -- C ABI of the B200 atmosphere-LUT accelerator for sfsim.
+ *
+ * Drop-in boundary for the `clj -T:build atmosphere-lut` path of wedesoft/sfsim
+ * (build.clj:84-87 -> src/clj/sfsim/atmosphere_lut.clj:43-105).  The reference has no
+ * native interface for this path; the conventions follow its only native precedent, the
+ * Jolt wrapper (src/c/sfsim/jolt.hh:1-77: extern "C", POD structs of doubles, arrays as
+ * pointer + count, no C++ types), with one deliberate difference: structs are passed by
+ * pointer and every entry point returns an int status (0 = ok) because CUDA can fail;
+ * atmlut_last_error() gives the message.  INTEGRATION.md shows the coffi/FFM binding.
+ *
+ * All vectors are double[3] (x, y, z) / RGB triples.  Tables are float32, RGB, row-major,
+ * first axis outermost -- the layout `pack-matrices` (matrix.clj:130-134) produces from the
+ * nested vectors of `make-lookup-table` (interpolate.clj:68-72).
+ *
+ * The library is not re-entrant: one call at a time from one thread (like the reference's
+ * single JVM thread driving libjolt).  There is no CPU fallback: without a CUDA device every
+ * compute entry point returns an error.
+ */
+#ifndef SFSIM_ATMOSPHERE_H
+#define SFSIM_ATMOSPHERE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* planet map of atmosphere.clj:64-67 / atmosphere_lut.clj:24-28 */
+typedef struct {
+  double centre[3];     /* :sfsim.sphere/centre (index maps assume the origin, atmosphere.clj:95-102) */
+  double radius;        /* :sfsim.sphere/radius */
+  double height;        /* :sfsim.atmosphere/height */
+  double brightness[3]; /* :sfsim.atmosphere/brightness */
+} atmlut_planet;
+
+/* scatter map of atmosphere.clj:35-39 */
+typedef struct {
+  double base[3]; /* ::scatter-base */
+  double scale;   /* ::scatter-scale */
+  double g;       /* ::scatter-g, 0.0 when the key is absent */
+  double quotient;/* ::scatter-quotient, 1.0 when the key is absent */
+} atmlut_scatter;
+
+/* the let-bindings of generate-atmosphere-luts, atmosphere_lut.clj:47-63 */
+typedef struct {
+  int height_size, elevation_size, light_elevation_size, heading_size; /* ray-scatter-shape */
+  int transmittance_height_size, transmittance_elevation_size;          /* transmittance-shape */
+  int surface_height_size, surface_sun_elevation_size;                  /* surface-radiance-shape */
+  int ray_steps, sphere_steps, iterations;
+  double intensity[3];
+} atmlut_config;
+
+/* ---- lifetime (jolt_init / jolt_destroy, jolt.cc:137-182) ---- */
+int atmlut_init(int device);                 /* select the CUDA device, create the stream */
+void atmlut_destroy(void);
+const char *atmlut_last_error(void);
+int atmlut_device_count(void);
+void atmlut_default_config(atmlut_config *cfg); /* shipped constants, atmosphere_lut.clj:47-63 */
+
+/* ---- the whole path: generate-atmosphere-luts (atmosphere_lut.clj:43-105) ----
+ * scatter = [mie rayleigh] (atmosphere_lut.clj:64); first-order tables use scatter[1] with its
+ * phase function and scatter[0] without (atmosphere_lut.clj:66-69).  Outputs are host buffers
+ * in FILE layout, ready for spit-floats (util.clj:236-240):
+ *   transmittance    float[Th][Te][3]
+ *   surface_radiance float[Sh][Ss][3]
+ *   ray_scatter, mie_strength float[H*S][E*A][3]   (convert-4d-to-2d, image.clj:299-312) */
+int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, const atmlut_config *cfg,
+                    float *transmittance, float *surface_radiance, float *ray_scatter, float *mie_strength);
+
+/* ---- device-resident builder: same computation, split so a host can shard it over GPUs ----
+ * Rank r of `world` computes a contiguous slab of every 4-D table; after each table the
+ * `allgather` callback (if set) must make buf[0 .. world*bytes_per_rank) identical on all ranks,
+ * given that this rank filled buf[rank*bytes_per_rank ..+bytes_per_rank).  `stream` is the
+ * cudaStream_t the slab was produced on; the callback must order its work after it. */
+typedef int (*atmlut_allgather_fn)(void *user, void *device_buf, size_t bytes_per_rank, void *stream);
+int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                          const atmlut_config *cfg, int rank, int world, void **builder);
+int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *user);
+int atmlut_builder_run(void *builder);        /* asynchronous on the library stream */
+int atmlut_builder_sync(void *builder);       /* wait for the stream */
+int atmlut_builder_download(void *builder, float *transmittance, float *surface_radiance, float *ray_scatter,
+                            float *mie_strength); /* file layout, as atmlut_generate */
+/* per-stage device time of the last run in milliseconds; names via atmlut_builder_stage_name */
+int atmlut_builder_stage_count(void *builder);
+const char *atmlut_builder_stage_name(void *builder, int stage);
+int atmlut_builder_stage_ms(void *builder, int stage, float *ms);
+/* sample counts of the last run: overall-extinction evaluations, 4-D lookups, 2-D lookups */
+int atmlut_builder_work(void *builder, double *esamples, double *lookups4d, double *lookups2d);
+int atmlut_builder_destroy(void *builder);
+
+/* ---- per-table entry points: make-lookup-table of each public function over its space ----
+ * (interpolate.clj:68-72 applied to atmosphere.clj:114-230).  Host float tables in and out,
+ * logical layout [..][3]. */
+int atmlut_transmittance_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                               const atmlut_config *cfg, float *out);
+int atmlut_surface_radiance_base_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                       const atmlut_config *cfg, float *out);
+/* ray-scatter of point-scatter-component (strength = 0) or strength-component (strength = 1) of
+ * scatter[component]; either output may be NULL */
+int atmlut_first_order_tables(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                              const atmlut_config *cfg, int component_a, int strength_a, float *out_a,
+                              int component_b, int strength_b, float *out_b);
+/* S source of point-scatter / surface-radiance: ds_a alone, or ds_a + ds_b * phase(scatter[phase_component], v.l)
+ * when ds_b != NULL (the closure of atmosphere_lut.clj:79-84) */
+int atmlut_point_scatter_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                               const atmlut_config *cfg, const float *ds_a, const float *ds_b, int phase_component,
+                               const float *de, float *out);
+int atmlut_surface_radiance_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                  const atmlut_config *cfg, const float *ds_a, const float *ds_b,
+                                  int phase_component, float *out);
+int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                             const atmlut_config *cfg, const float *dj, float *out);
+/* re-tabulation of closures (atmosphere_lut.clj:94-101): out[i] = lookup(a, g(i)) [+ lookup(b, g(i))],
+ * g = forward o backward of the space.  which: 0 = ray-scatter (4-D), 1 = surface-radiance, 2 = transmittance */
+int atmlut_resample_table(const atmlut_planet *planet, const atmlut_config *cfg, int which, const float *a,
+                          const float *b, float *out);
+
+/* ---- batch point evaluators: the public functions of sfsim.atmosphere at arbitrary arguments ---- */
+/* transmittance, 5-arity (atmosphere.clj:118-125): x -> x0 */
+int atmlut_transmittance_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                               int count, const double *x, const double *x0, double *out);
+/* transmittance, 6-arity (atmosphere.clj:126-128): x along v to the shell (above != 0) or the ground */
+int atmlut_transmittance_dir_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                                   int count, const double *x, const double *v, const int *above, double *out);
+/* surface-radiance-base (atmosphere.clj:131-137) */
+int atmlut_surface_radiance_base_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                                       const double *intensity, int count, const double *x, const double *l,
+                                       double *out);
+/* kind 0: point-scatter-component of scatter[component] (atmosphere.clj:170-174)
+ * kind 1: strength-component of scatter[component]      (atmosphere.clj:177-182)
+ * kind 2: point-scatter-base                            (atmosphere.clj:185-189) */
+int atmlut_point_scatter_first_order_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                           int kind, int component, int steps, const double *intensity, int count,
+                                           const double *x, const double *v, const double *l, double *out);
+/* ray-scatter (atmosphere.clj:192-200) of a first-order point-scatter function (kind/component as above) */
+int atmlut_ray_scatter_first_order_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int kind,
+                                         int component, int steps, const double *intensity, int count,
+                                         const double *x, const double *v, const double *l, const int *above,
+                                         double *out);
+
+/* ---- index maps (atmosphere.clj:233-422), evaluated on the device in double precision ---- */
+/* which: 0 = ray-scatter-space [4 indices; point, direction, light, above]
+ *        1 = surface-radiance-space [2 indices; point, light]
+ *        2 = transmittance-space [2 indices; point, direction, above]
+ * shape: the table shape of that space.  Unused inputs/outputs may be NULL. */
+int atmlut_index_forward_batch(const atmlut_planet *planet, int which, const int *shape, int count,
+                               const double *point, const double *direction, const double *light, const int *above,
+                               double *indices);
+int atmlut_index_backward_batch(const atmlut_planet *planet, int which, const int *shape, int count,
+                                const double *indices, double *point, double *direction, double *light, int *above);
+
+/* interpolate-value (interpolate.clj:87-98) on a float table of `ncomp`-vectors, dims <= 4 */
+int atmlut_interpolate_batch(const float *table, const int *shape, int dims, int ncomp, int count,
+                             const double *coords, float *out);
+
+/* ---- output (util.clj:227-240, image.clj:299-312) ---- */
+int atmlut_convert_4d_to_2d(const float *in, const int *shape, int ncomp, float *out);
+int atmlut_write_floats(const char *path, const float *data, long count);
+long atmlut_read_floats(const char *path, float *data, long max_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -617,7 +617,7 @@ def generate_atmosphere_luts(pl, mie, rayleigh, cfg, iterations=5, record=None, 
     M1 = table_first_order(pl, scatters, cfg, mie, 1)                            # :78
     dS = SSourceSpec(R1, M1, mie)                                                # :79-84
     S = R1                                                                       # :85
-    rec.update(T=T, E0=dE, R1=R1, M1=M1)
+    rec.update(T=T, Ebase=dE, R1=R1, M1=M1)
     for it in range(iterations):                                                 # :86
         if log:
             log("Iteration %d/%d" % (it + 1, iterations))

@@ -1,0 +1,156 @@
+"""Host-side mirror of sfsim.atmosphere-lut (src/clj/sfsim/atmosphere_lut.clj) over the C ABI.
+
+`generate_atmosphere_luts` is the drop-in for `clj -T:build atmosphere-lut` (build.clj:84-87): it
+produces the four `data/atmosphere/*.scatter` files with the same names, shapes and byte layout.
+`AtmosphereLutBuilder` is the device-resident form used for benchmarking and for sharding one
+build over the GPUs of a box (one process per GPU, torch.distributed/NCCL all-gather per table).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+# atmosphere_lut.clj:20-40
+radius = 6378000.0
+height = 35000.0
+earth = {"centre": (0.0, 0.0, 0.0), "radius": radius, "height": height, "brightness": (0.3, 0.3, 0.3)}
+mie = {"base": (2e-5, 2e-5, 2e-5), "scale": 1200.0, "g": 0.76, "quotient": 0.9}
+rayleigh = {"base": (5.8e-6, 13.5e-6, 33.1e-6), "scale": 8000.0}
+
+FILE_NAMES = ("transmittance.scatter", "surface-radiance.scatter", "ray-scatter.scatter", "mie-strength.scatter")
+
+
+def output_shapes(cfg):
+    """File-layout shapes of the four outputs."""
+    h, e, s, a = cfg.ray_scatter_shape
+    return (cfg.transmittance_shape + (3,), cfg.surface_radiance_shape + (3,), (h * s, e * a, 3), (h * s, e * a, 3))
+
+
+def allocate_outputs(cfg, pinned=False):
+    shapes = output_shapes(cfg)
+    if pinned:
+        import torch
+        return [torch.empty(s, dtype=torch.float32).pin_memory().numpy() for s in shapes]
+    return [np.empty(s, dtype=np.float32) for s in shapes]
+
+
+def generate_tables(planet=earth, scatter=(mie, rayleigh), cfg=None, out=None):
+    """generate-atmosphere-luts up to (not including) the file writes; returns the four float32 arrays
+    in file layout.  One call into the library: atmlut_generate."""
+    lib = _lib.load()
+    cfg = cfg or _lib.default_config()
+    out = out or allocate_outputs(cfg)
+    pl = _lib.make_planet(planet)
+    sc = _lib.make_scatter_array(scatter)
+    check(lib.atmlut_generate(C.byref(pl), sc, len(scatter), C.byref(cfg), *[_lib.ptr(o) for o in out]))
+    return out
+
+
+def write_tables(tables, out_dir):
+    """spit-floats of the four tables (atmosphere_lut.clj:102-105)."""
+    lib = _lib.load()
+    os.makedirs(out_dir, exist_ok=True)
+    paths = []
+    for name, t in zip(FILE_NAMES, tables):
+        path = os.path.join(out_dir, name)
+        t = _lib.f32(t)
+        check(lib.atmlut_write_floats(path.encode(), _lib.ptr(t), C.c_long(t.size)))
+        paths.append(path)
+    return paths
+
+
+def generate_atmosphere_luts(out_dir="data/atmosphere", planet=earth, scatter=(mie, rayleigh), cfg=None):
+    """Program to generate lookup tables for atmospheric scattering (atmosphere_lut.clj:43-105)."""
+    return write_tables(generate_tables(planet, scatter, cfg), out_dir)
+
+
+class AtmosphereLutBuilder:
+    """Device-resident build.  With world > 1 each rank computes a contiguous slab of every 4-D table and
+    the tables are reassembled with one all-gather each through torch.distributed (NCCL on GPUs)."""
+
+    def __init__(self, planet=earth, scatter=(mie, rayleigh), cfg=None, rank=0, world=1, device=None,
+                 process_group=None):
+        self.lib = _lib.load()
+        self.cfg = cfg or _lib.default_config()
+        self.rank, self.world = rank, world
+        if device is not None:
+            check(self.lib.atmlut_init(int(device)))
+        pl = _lib.make_planet(planet)
+        sc = _lib.make_scatter_array(scatter)
+        self.handle = C.c_void_p()
+        check(self.lib.atmlut_builder_create(C.byref(pl), sc, len(scatter), C.byref(self.cfg), rank, world,
+                                             C.byref(self.handle)))
+        self._callback = None
+        self.gathers = 0
+        if world > 1:
+            self._install_allgather(process_group)
+
+    def _install_allgather(self, process_group):
+        import torch
+        import torch.distributed as dist
+
+        class _Raw:
+            """__cuda_array_interface__ view of a raw device range, so torch can wrap the library's table."""
+
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False),
+                                                 "version": 3, "strides": None}
+
+        def allgather(_user, buf, bytes_per_rank, stream):
+            try:
+                ext = torch.cuda.ExternalStream(stream)
+                with torch.cuda.stream(ext):
+                    full = torch.as_tensor(_Raw(buf, bytes_per_rank * self.world), device="cuda")
+                    mine = full[self.rank * (bytes_per_rank // 4):(self.rank + 1) * (bytes_per_rank // 4)]
+                    dist.all_gather_into_tensor(full, mine, group=process_group)
+                self.gathers += 1
+                return 0
+            except Exception as exc:  # surfaces as "allgather callback failed" from the library
+                import traceback
+                traceback.print_exc()
+                self._error = exc
+                return 1
+
+        self._callback = _lib.ALLGATHER_FN(allgather)
+        check(self.lib.atmlut_builder_set_allgather(self.handle, self._callback, None))
+
+    def run(self):
+        """Enqueue one full build on the library stream (asynchronous)."""
+        check(self.lib.atmlut_builder_run(self.handle))
+
+    def sync(self):
+        check(self.lib.atmlut_builder_sync(self.handle))
+
+    def download(self, out=None):
+        out = out or allocate_outputs(self.cfg)
+        check(self.lib.atmlut_builder_download(self.handle, *[_lib.ptr(o) for o in out]))
+        return out
+
+    def stage_times(self):
+        """[(stage name, device milliseconds)] of the last run."""
+        n = self.lib.atmlut_builder_stage_count(self.handle)
+        res = []
+        for i in range(n):
+            ms = C.c_float()
+            check(self.lib.atmlut_builder_stage_ms(self.handle, i, C.byref(ms)))
+            res.append((self.lib.atmlut_builder_stage_name(self.handle, i).decode(), ms.value))
+        return res
+
+    def work(self):
+        e, l4, l2 = C.c_double(), C.c_double(), C.c_double()
+        check(self.lib.atmlut_builder_work(self.handle, C.byref(e), C.byref(l4), C.byref(l2)))
+        return {"esamples": e.value, "lookups4d": l4.value, "lookups2d": l2.value}
+
+    def close(self):
+        if self.handle:
+            self.lib.atmlut_builder_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

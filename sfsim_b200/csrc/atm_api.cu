@@ -1,0 +1,738 @@
+// C ABI of libsfsim_atmosphere.so (include/sfsim_atmosphere.h): parameter validation, device
+// buffers, and the host orchestration of generate-atmosphere-luts (atmosphere_lut.clj:43-105).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sfsim_atmosphere.h"
+#include "atm_api_internal.h"
+#include "atm_tables.h"
+
+namespace atm {
+
+// ------------------------------------------------------------------ global state (jolt_init-style singletons)
+
+static thread_local std::string g_error;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+
+int fail(const std::string &msg) {
+  g_error = msg;
+  return 1;
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+
+int ensure_init() {
+  if (g_device >= 0) return 0;
+  return atmlut_init(0);
+}
+
+cudaStream_t stream() { return g_stream; }
+
+// ------------------------------------------------------------------ parameters
+
+int make_planet_medium(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, Params &P) {
+  if (!planet) return fail("planet is NULL");
+  if (n < 0 || n > 2) return fail("scatter count must be 0, 1 or 2");
+  if (n > 0 && !scatter) return fail("scatter is NULL");
+  if (!(planet->radius > 0) || !(planet->height > 0)) return fail("planet radius and height must be positive");
+  memset(&P, 0, sizeof(P));
+  P.planet.radius = planet->radius;
+  P.planet.height = planet->height;
+  for (int i = 0; i < 3; i++) P.planet.brightness[i] = planet->brightness[i];
+  P.medium.n = n;
+  for (int c = 0; c < 2; c++) {
+    P.medium.scale[c] = 1.0;
+    P.medium.quotient[c] = 1.0;
+  }
+  for (int c = 0; c < n; c++) {
+    if (!(scatter[c].scale > 0)) return fail("scatter scale must be positive");
+    if (scatter[c].quotient == 0) return fail("scatter quotient must not be zero");
+    for (int i = 0; i < 3; i++) P.medium.base[c][i] = scatter[c].base[i];
+    P.medium.scale[c] = scatter[c].scale;
+    P.medium.g[c] = scatter[c].g;
+    P.medium.quotient[c] = scatter[c].quotient;
+  }
+  // fast sampler constants (atm_device.cuh)
+  const double R = planet->radius, Rt = planet->radius + planet->height;
+  const double delta = R / 4096.0;
+  const double Rp = R - delta;
+  P.fast.rp2 = Rp * Rp;
+  P.fast.inv_rp2 = 1.0 / (Rp * Rp);
+  P.fast.poly = ((Rt * Rt - Rp * Rp) / (Rp * Rp) <= 0.05) ? 1 : 0;
+  const double log2e = 1.4426950408889634;
+  for (int c = 0; c < 2; c++) {
+    P.fast.k[c] = (float)(-Rp * log2e / P.medium.scale[c]);
+    P.fast.b[c] = (float)(delta * log2e / P.medium.scale[c]);
+    for (int i = 0; i < 3; i++) P.fast.ext[c][i] = (float)(P.medium.base[c][i] / P.medium.quotient[c]);
+  }
+  for (int i = 0; i < 3; i++) P.intensity[i] = 1.0;
+  return 0;
+}
+
+int make_params(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, const atmlut_config *cfg,
+                Params &P) {
+  if (make_planet_medium(planet, scatter, n, P)) return 1;
+  if (!cfg) return fail("config is NULL");
+  if (planet->centre[0] != 0 || planet->centre[1] != 0 || planet->centre[2] != 0)
+    return fail("table builders need the planet centre at the origin (the index maps assume it, atmosphere.clj:95-102)");
+  const int sizes[8] = {cfg->height_size, cfg->elevation_size, cfg->light_elevation_size, cfg->heading_size,
+                        cfg->transmittance_height_size, cfg->transmittance_elevation_size, cfg->surface_height_size,
+                        cfg->surface_sun_elevation_size};
+  for (int i = 0; i < 8; i++)
+    if (sizes[i] < 2) return fail("every table axis needs at least 2 entries");
+  if (cfg->ray_steps < 1 || cfg->ray_steps > kMaxSteps) return fail("ray_steps must be in [1, 256]");
+  if (cfg->sphere_steps < 2) return fail("sphere_steps must be at least 2");
+  for (int i = 0; i < 4; i++) P.shapes.s4[i] = sizes[i];
+  P.shapes.st[0] = sizes[4];
+  P.shapes.st[1] = sizes[5];
+  P.shapes.se[0] = sizes[6];
+  P.shapes.se[1] = sizes[7];
+  P.shapes.ray_steps = cfg->ray_steps;
+  P.shapes.sphere_steps = cfg->sphere_steps;
+  for (int i = 0; i < 3; i++) P.intensity[i] = cfg->intensity[i];
+  return 0;
+}
+
+// Direction list of spherical-integral (sphere.clj:70-93) for normal (1, 0, 0), in evaluation order.
+// Every table point is x = (r, 0, 0), so oriented-matrix (matrix.clj:207-213) has rows n = (1,0,0),
+// o1 = orthogonal(n) = normalize(n x e1) = (0,0,1) (quaternion.clj:166-171), o2 = n x o1 = (0,-1,0).
+// Ring counts ceil(sin(theta) * phi_steps) are evaluated here in host double precision.
+void sphere_directions(int theta_steps, int phi_steps, double theta_range, std::vector<double> &dirs,
+                       std::vector<double> &weights) {
+  dirs.clear();
+  weights.clear();
+  const double delta2 = theta_range / (double)theta_steps / 2;
+  const double m[9] = {1, 0, 0, 0, 0, 1, 0, -1, 0};
+  for (int k = 0; k < theta_steps; k++) {
+    double theta = theta_range * ((0.5 + (double)k) / (double)theta_steps);
+    double factor = cos(theta - delta2) - cos(theta + delta2);
+    int ringsteps = (int)ceil(sin(theta) * (double)phi_steps);
+    double weight = (2 * kPi) / (double)ringsteps;
+    for (int j = 0; j < ringsteps; j++) {
+      double phi = 2 * kPi * ((0.5 + (double)j) / (double)ringsteps);
+      double x = cos(theta), y = sin(theta) * cos(phi), z = sin(theta) * sin(phi);
+      dirs.push_back(m[0] * x + m[3] * y + m[6] * z);
+      dirs.push_back(m[1] * x + m[4] * y + m[7] * z);
+      dirs.push_back(m[2] * x + m[5] * y + m[8] * z);
+      weights.push_back(factor * weight);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ builder
+
+struct Stage {
+  std::string name;
+  cudaEvent_t begin, end;
+};
+
+struct Builder {
+  Params P;
+  int iterations = 0;
+  int rank = 0, world = 1;
+  int n_he = 0, he_per_rank = 0, he_begin = 0, he_count = 0;
+  long long ntex = 0, n4 = 0, n4_pad = 0, nt = 0, ne = 0;
+  atmlut_allgather_fn allgather = nullptr;
+  void *allgather_user = nullptr;
+  // device tables (float4)
+  float4 *T = nullptr, *dE = nullptr, *dE_new = nullptr, *Eacc = nullptr, *Eacc_new = nullptr;
+  float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
+  float *file_T = nullptr, *file_E = nullptr, *file_S = nullptr, *file_M = nullptr;
+  double *sphere_dirs = nullptr, *sphere_w = nullptr, *half_dirs = nullptr, *half_w = nullptr;
+  int n_sphere = 0, n_half = 0;
+  DirInfo *dir_info = nullptr;
+  HalfDirInfo *half_info = nullptr;
+  unsigned long long *counter = nullptr;
+  std::vector<Stage> stages;
+  size_t stage_cursor = 0;
+  bool ran = false;
+  double esamples = 0, lookups4d = 0, lookups2d = 0;
+
+  ~Builder() {
+    void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dJ, S, S_new, file_T, file_E, file_S, file_M,
+                    sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter};
+    for (void *p : ptrs)
+      if (p) cudaFree(p);
+    for (auto &s : stages) {
+      cudaEventDestroy(s.begin);
+      cudaEventDestroy(s.end);
+    }
+  }
+};
+
+template <typename T>
+static int dev_alloc(T *&p, size_t count) {
+  CUDA_TRY(cudaMalloc((void **)&p, count * sizeof(T)));
+  return 0;
+}
+
+static int upload(double *&dst, const std::vector<double> &src) {
+  if (dev_alloc(dst, src.size())) return 1;
+  CUDA_TRY(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+static int builder_alloc(Builder &b) {
+  const Params &P = b.P;
+  b.n_he = P.shapes.s4[0] * P.shapes.s4[1];
+  b.ntex = (long long)P.shapes.s4[2] * P.shapes.s4[3];
+  b.he_per_rank = (b.n_he + b.world - 1) / b.world;
+  b.he_begin = b.rank * b.he_per_rank;
+  b.he_count = std::max(0, std::min(b.n_he, b.he_begin + b.he_per_rank) - b.he_begin);
+  b.n4 = b.n_he * b.ntex;
+  b.n4_pad = (long long)b.he_per_rank * b.world * b.ntex;
+  b.nt = (long long)P.shapes.st[0] * P.shapes.st[1];
+  b.ne = (long long)P.shapes.se[0] * P.shapes.se[1];
+  float4 **four[] = {&b.R1, &b.M1, &b.dS, &b.dJ, &b.S, &b.S_new};
+  for (auto p : four) {
+    if (dev_alloc(*p, (size_t)b.n4_pad)) return 1;
+    CUDA_TRY(cudaMemsetAsync(*p, 0, (size_t)b.n4_pad * sizeof(float4), g_stream));
+  }
+  float4 **two[] = {&b.dE, &b.dE_new, &b.Eacc, &b.Eacc_new};
+  for (auto p : two)
+    if (dev_alloc(*p, (size_t)b.ne)) return 1;
+  if (dev_alloc(b.T, (size_t)b.nt)) return 1;
+  if (dev_alloc(b.file_T, (size_t)b.nt * 3)) return 1;
+  if (dev_alloc(b.file_E, (size_t)b.ne * 3)) return 1;
+  if (dev_alloc(b.file_S, (size_t)b.n4 * 3)) return 1;
+  if (dev_alloc(b.file_M, (size_t)b.n4 * 3)) return 1;
+  if (dev_alloc(b.counter, 2)) return 1;
+  std::vector<double> dirs, w;
+  sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);  // sphere.clj:102-105
+  b.n_sphere = (int)w.size();
+  if (b.n_sphere > kMaxDirs) return fail("sphere_steps too large for the point-scatter kernel");
+  if (upload(b.sphere_dirs, dirs) || upload(b.sphere_w, w)) return 1;
+  // surface-radiance is called with ray-steps as its sphere steps (atmosphere_lut.clj:89)
+  sphere_directions(P.shapes.ray_steps >> 2, P.shapes.ray_steps, kPi / 2, dirs, w);  // sphere.clj:96-99
+  b.n_half = (int)w.size();
+  if (b.n_half > 0 && (upload(b.half_dirs, dirs) || upload(b.half_w, w))) return 1;
+  if (dev_alloc(b.dir_info, (size_t)P.shapes.s4[0] * b.n_sphere)) return 1;
+  if (dev_alloc(b.half_info, (size_t)P.shapes.se[0] * std::max(1, b.n_half))) return 1;
+  return 0;
+}
+
+static int stage_begin(Builder &b, const std::string &name) {
+  if (b.stage_cursor == b.stages.size()) {
+    Stage s;
+    s.name = name;
+    CUDA_TRY(cudaEventCreate(&s.begin));
+    CUDA_TRY(cudaEventCreate(&s.end));
+    b.stages.push_back(s);
+  }
+  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].begin, g_stream));
+  return 0;
+}
+
+static int stage_end(Builder &b) {
+  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, g_stream));
+  b.stage_cursor++;
+  return 0;
+}
+
+static int gather(Builder &b, float4 *table) {
+  if (b.world <= 1 || !b.allgather) return 0;
+  size_t bytes = (size_t)b.he_per_rank * b.ntex * sizeof(float4);
+  if (b.allgather(b.allgather_user, table, bytes, (void *)g_stream)) return fail("allgather callback failed");
+  return 0;
+}
+
+#define TRY(expr)          \
+  do {                     \
+    if (expr) return 1;    \
+  } while (0)
+#define LAUNCH(expr) CUDA_TRY(expr)
+
+// generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below)
+static int builder_run(Builder &b) {
+  const Params &P = b.P;
+  cudaStream_t st = g_stream;
+  b.stage_cursor = 0;
+  CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
+  const long long slab_begin = (long long)b.he_begin * b.ntex, slab_count = (long long)b.he_count * b.ntex;
+  (void)slab_begin;
+  (void)slab_count;
+
+  TRY(stage_begin(b, "transmittance+surface_radiance_base"));
+  LAUNCH(launch_transmittance_table(P, b.T, st));                                     // :74
+  LAUNCH(launch_surface_radiance_base(P, b.dE, st));                                  // :75
+  CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), st));            // :76 E = 0
+  LAUNCH(launch_point_scatter_prepare(P, b.sphere_dirs, b.n_sphere, b.dir_info, st));
+  if (b.n_half > 0) LAUNCH(launch_surface_radiance_prepare(P, b.half_dirs, b.n_half, b.half_info, st));
+  TRY(stage_end(b));
+
+  TRY(stage_begin(b, "first_order"));
+  FirstOrderOut rayleigh = {b.R1, 1, 0};                                              // :68,71,77
+  FirstOrderOut mie_strength = {b.M1, 0, 1};                                          // :69,72,78
+  LAUNCH(launch_first_order(P, b.he_begin, b.he_count, rayleigh, mie_strength, b.counter, st));
+  TRY(stage_end(b));
+  TRY(stage_begin(b, "first_order_allgather"));
+  TRY(gather(b, b.R1));
+  TRY(gather(b, b.M1));
+  TRY(stage_end(b));
+
+  SSource ds = {b.R1, b.M1, P.medium.g[0]};                                           // :79-84
+  const float4 *s_cur = b.R1;                                                         // :85
+  for (int it = 0; it < b.iterations; it++) {                                         // :86
+    char name[64];
+    snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
+    TRY(stage_begin(b, name));
+    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, ds, b.dE, b.sphere_dirs, b.sphere_w, b.n_sphere,
+                                b.dir_info, b.dJ, st));                              // :88,90
+    TRY(stage_end(b));
+    snprintf(name, sizeof name, "iter%d_point_scatter_allgather", it + 1);
+    TRY(stage_begin(b, name));
+    TRY(gather(b, b.dJ));
+    TRY(stage_end(b));
+    snprintf(name, sizeof name, "iter%d_surface_radiance", it + 1);
+    TRY(stage_begin(b, name));
+    if (b.n_half > 0)
+      LAUNCH(launch_surface_radiance(P, ds, b.half_dirs, b.half_w, b.n_half, b.half_info, b.dE_new, st));  // :89,92
+    else
+      CUDA_TRY(cudaMemsetAsync(b.dE_new, 0, (size_t)b.ne * sizeof(float4), st));
+    TRY(stage_end(b));
+    snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
+    TRY(stage_begin(b, name));
+    LAUNCH(launch_ray_scatter(P, b.he_begin, b.he_count, b.dJ, b.dS, b.counter + 1, st));  // :91,93
+    TRY(stage_end(b));
+    snprintf(name, sizeof name, "iter%d_ray_scatter_allgather", it + 1);
+    TRY(stage_begin(b, name));
+    TRY(gather(b, b.dS));
+    TRY(stage_end(b));
+    snprintf(name, sizeof name, "iter%d_accumulate", it + 1);
+    TRY(stage_begin(b, name));
+    std::swap(b.dE, b.dE_new);
+    LAUNCH(launch_resample_2d(P, 1, it == 0 ? nullptr : b.Eacc, b.dE, b.Eacc_new, nullptr, st));  // :94-95
+    std::swap(b.Eacc, b.Eacc_new);
+    LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, b.dS, b.S_new, nullptr, st));        // :96-97
+    std::swap(b.S, b.S_new);
+    s_cur = b.S;
+    ds = SSource{b.dS, nullptr, 0.0};
+    TRY(stage_end(b));
+  }
+  TRY(stage_begin(b, "final_resample"));
+  LAUNCH(launch_resample_2d(P, 2, b.T, nullptr, nullptr, b.file_T, st));              // :98,102
+  LAUNCH(launch_resample_2d(P, 1, b.Eacc, nullptr, nullptr, b.file_E, st));           // :99,103
+  LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, nullptr, nullptr, b.file_S, st));      // :100,104
+  LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, st));       // :101,105
+  TRY(stage_end(b));
+  b.ran = true;
+  return 0;
+}
+
+}  // namespace atm
+
+using namespace atm;
+
+// ------------------------------------------------------------------ C ABI: lifetime
+
+extern "C" int atmlut_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int atmlut_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(std::string("no CUDA device available (there is no CPU fallback)") +
+                (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string()));
+  if (device < 0 || device >= n) return fail("invalid device index");
+  CUDA_TRY(cudaSetDevice(device));
+  if (g_stream && g_device != device) {
+    cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+  }
+  if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_device = device;
+  return 0;
+}
+
+extern "C" void atmlut_destroy(void) {
+  if (g_stream) {
+    cudaStreamSynchronize(g_stream);
+    cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+  }
+  g_device = -1;
+}
+
+extern "C" const char *atmlut_last_error(void) { return g_error.c_str(); }
+
+extern "C" void atmlut_default_config(atmlut_config *cfg) {
+  // atmosphere_lut.clj:47-63
+  cfg->height_size = 32;
+  cfg->elevation_size = 127;
+  cfg->light_elevation_size = 32;
+  cfg->heading_size = 8;
+  cfg->transmittance_height_size = 64;
+  cfg->transmittance_elevation_size = 255;
+  cfg->surface_height_size = 16;
+  cfg->surface_sun_elevation_size = 63;
+  cfg->ray_steps = 100;
+  cfg->sphere_steps = 15;
+  cfg->iterations = 5;
+  cfg->intensity[0] = cfg->intensity[1] = cfg->intensity[2] = 1.0;
+}
+
+// ------------------------------------------------------------------ C ABI: builder
+
+extern "C" int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                     const atmlut_config *cfg, int rank, int world, void **builder) {
+  if (!builder) return fail("builder is NULL");
+  *builder = nullptr;
+  if (ensure_init()) return 1;
+  if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
+  if (world < 1 || rank < 0 || rank >= world) return fail("invalid rank/world");
+  Builder *b = new Builder();
+  if (make_params(planet, scatter, n, cfg, b->P)) {
+    delete b;
+    return 1;
+  }
+  if (cfg->iterations < 0) {
+    delete b;
+    return fail("iterations must not be negative");
+  }
+  b->iterations = cfg->iterations;
+  b->rank = rank;
+  b->world = world;
+  if (builder_alloc(*b)) {
+    delete b;
+    return 1;
+  }
+  *builder = b;
+  return 0;
+}
+
+extern "C" int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *user) {
+  if (!builder) return fail("builder is NULL");
+  Builder *b = (Builder *)builder;
+  b->allgather = fn;
+  b->allgather_user = user;
+  return 0;
+}
+
+extern "C" int atmlut_builder_run(void *builder) {
+  if (!builder) return fail("builder is NULL");
+  Builder *b = (Builder *)builder;
+  if (b->world > 1 && !b->allgather) return fail("world > 1 needs an allgather callback");
+  return builder_run(*b);
+}
+
+extern "C" int atmlut_builder_sync(void *builder) {
+  (void)builder;
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+extern "C" int atmlut_builder_download(void *builder, float *transmittance, float *surface_radiance,
+                                       float *ray_scatter, float *mie_strength) {
+  if (!builder) return fail("builder is NULL");
+  Builder *b = (Builder *)builder;
+  if (!b->ran) return fail("builder has not run");
+  if (transmittance)
+    CUDA_TRY(cudaMemcpyAsync(transmittance, b->file_T, (size_t)b->nt * 12, cudaMemcpyDeviceToHost, g_stream));
+  if (surface_radiance)
+    CUDA_TRY(cudaMemcpyAsync(surface_radiance, b->file_E, (size_t)b->ne * 12, cudaMemcpyDeviceToHost, g_stream));
+  if (ray_scatter)
+    CUDA_TRY(cudaMemcpyAsync(ray_scatter, b->file_S, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, g_stream));
+  if (mie_strength)
+    CUDA_TRY(cudaMemcpyAsync(mie_strength, b->file_M, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, g_stream));
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+extern "C" int atmlut_builder_stage_count(void *builder) {
+  if (!builder) return 0;
+  return (int)((Builder *)builder)->stages.size();
+}
+
+extern "C" const char *atmlut_builder_stage_name(void *builder, int stage) {
+  Builder *b = (Builder *)builder;
+  if (!b || stage < 0 || stage >= (int)b->stages.size()) return "";
+  return b->stages[stage].name.c_str();
+}
+
+extern "C" int atmlut_builder_stage_ms(void *builder, int stage, float *ms) {
+  Builder *b = (Builder *)builder;
+  if (!b || stage < 0 || stage >= (int)b->stages.size()) return fail("invalid stage");
+  CUDA_TRY(cudaEventSynchronize(b->stages[stage].end));
+  CUDA_TRY(cudaEventElapsedTime(ms, b->stages[stage].begin, b->stages[stage].end));
+  return 0;
+}
+
+extern "C" int atmlut_builder_work(void *builder, double *esamples, double *lookups4d, double *lookups2d) {
+  Builder *b = (Builder *)builder;
+  if (!b || !b->ran) return fail("builder has not run");
+  unsigned long long c[2];
+  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, g_stream));
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  std::vector<DirInfo> info((size_t)b->P.shapes.s4[0] * b->n_sphere);
+  CUDA_TRY(cudaMemcpy(info.data(), b->dir_info, info.size() * sizeof(DirInfo), cudaMemcpyDeviceToHost));
+  const Params &P = b->P;
+  const double steps = P.shapes.ray_steps;
+  double surf_dirs = 0;  // surface-hitting directions summed over this rank's (height, elevation) pairs
+  for (int he = b->he_begin; he < b->he_begin + b->he_count; he++)
+    for (int d = 0; d < b->n_sphere; d++) surf_dirs += info[(size_t)(he / P.shapes.s4[1]) * b->n_sphere + d].surface;
+  double surf_hd = 0;
+  for (auto &i : info) surf_hd += i.surface;
+  const double slab = (double)b->he_count * b->ntex;
+  const double it = b->iterations;
+  if (esamples) *esamples = (double)c[0] + (double)c[1] + (b->nt + b->ne + surf_hd) * steps;
+  if (lookups4d)
+    *lookups4d = slab * b->n_sphere * (it > 0 ? it + 1 : 0) + (double)b->ne * b->n_half * (it > 0 ? it + 1 : 0) +
+                 slab * steps * it + (double)b->n4 * (2 * it + 2);
+  if (lookups2d) *lookups2d = surf_dirs * b->ntex * it + (double)b->ne * (2 * it - (it > 0 ? 1 : 0) + 1) + b->nt;
+  return 0;
+}
+
+extern "C" int atmlut_builder_destroy(void *builder) {
+  if (!builder) return 0;
+  cudaStreamSynchronize(g_stream);
+  delete (Builder *)builder;
+  return 0;
+}
+
+extern "C" int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                               const atmlut_config *cfg, float *transmittance, float *surface_radiance,
+                               float *ray_scatter, float *mie_strength) {
+  void *b = nullptr;
+  if (atmlut_builder_create(planet, scatter, n, cfg, 0, 1, &b)) return 1;
+  int rc = atmlut_builder_run(b);
+  if (!rc) rc = atmlut_builder_download(b, transmittance, surface_radiance, ray_scatter, mie_strength);
+  atmlut_builder_destroy(b);
+  return rc;
+}
+
+// ------------------------------------------------------------------ C ABI: per-table entry points
+
+namespace {
+
+struct DevTables {
+  std::vector<void *> ptrs;
+  ~DevTables() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(T *&p, size_t count) {
+    if (dev_alloc(p, count ? count : 1)) return 1;
+    ptrs.push_back(p);
+    return 0;
+  }
+  // host RGB float table -> device float4 table
+  int upload_rgb(const float *host, long long texels, float4 *&dev) {
+    float *staging = nullptr;
+    if (alloc(staging, (size_t)texels * 3) || alloc(dev, (size_t)texels)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(staging, host, (size_t)texels * 12, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(launch_rgb_to_float4(staging, dev, texels, g_stream));
+    return 0;
+  }
+  int download_rgb(const float4 *dev, long long texels, float *host) {
+    float *staging = nullptr;
+    if (alloc(staging, (size_t)texels * 3)) return 1;
+    CUDA_TRY(launch_float4_to_rgb(dev, staging, texels, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(host, staging, (size_t)texels * 12, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return 0;
+  }
+  int upload_doubles(const std::vector<double> &src, double *&dev) {
+    if (alloc(dev, src.size())) return 1;
+    CUDA_TRY(cudaMemcpyAsync(dev, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return 0;
+  }
+};
+
+long long n4_of(const Params &P) { return (long long)P.shapes.s4[0] * P.shapes.s4[1] * P.shapes.s4[2] * P.shapes.s4[3]; }
+
+}  // namespace
+
+extern "C" int atmlut_transmittance_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                          const atmlut_config *cfg, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (!out) return fail("out is NULL");
+  DevTables d;
+  float4 *t = nullptr;
+  long long nt = (long long)P.shapes.st[0] * P.shapes.st[1];
+  if (d.alloc(t, (size_t)nt)) return 1;
+  CUDA_TRY(launch_transmittance_table(P, t, g_stream));
+  return d.download_rgb(t, nt, out);
+}
+
+extern "C" int atmlut_surface_radiance_base_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                                  const atmlut_config *cfg, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (!out) return fail("out is NULL");
+  DevTables d;
+  float4 *t = nullptr;
+  long long ne = (long long)P.shapes.se[0] * P.shapes.se[1];
+  if (d.alloc(t, (size_t)ne)) return 1;
+  CUDA_TRY(launch_surface_radiance_base(P, t, g_stream));
+  return d.download_rgb(t, ne, out);
+}
+
+extern "C" int atmlut_first_order_tables(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                         const atmlut_config *cfg, int component_a, int strength_a, float *out_a,
+                                         int component_b, int strength_b, float *out_b) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (n < 1) return fail("first-order tables need at least one scatter component");
+  if ((out_a && (component_a < 0 || component_a >= n)) || (out_b && (component_b < 0 || component_b >= n)))
+    return fail("component index out of range");
+  DevTables d;
+  float4 *ta = nullptr, *tb = nullptr;
+  const long long n4 = n4_of(P);
+  if (out_a && d.alloc(ta, (size_t)n4)) return 1;
+  if (out_b && d.alloc(tb, (size_t)n4)) return 1;
+  FirstOrderOut oa = {ta, component_a, strength_a}, ob = {tb, component_b, strength_b};
+  CUDA_TRY(launch_first_order(P, 0, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
+  if (out_a && d.download_rgb(ta, n4, out_a)) return 1;
+  if (out_b && d.download_rgb(tb, n4, out_b)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                          const atmlut_config *cfg, const float *ds_a, const float *ds_b,
+                                          int phase_component, const float *de, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (!ds_a || !de || !out) return fail("ds_a, de and out must not be NULL");
+  if (ds_b && (phase_component < 0 || phase_component >= n)) return fail("phase component out of range");
+  DevTables d;
+  const long long n4 = n4_of(P), ne = (long long)P.shapes.se[0] * P.shapes.se[1];
+  float4 *a = nullptr, *b = nullptr, *e = nullptr, *o = nullptr;
+  if (d.upload_rgb(ds_a, n4, a) || (ds_b && d.upload_rgb(ds_b, n4, b)) || d.upload_rgb(de, ne, e) ||
+      d.alloc(o, (size_t)n4))
+    return 1;
+  std::vector<double> dirs, w;
+  sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);
+  if ((int)w.size() > kMaxDirs) return fail("sphere_steps too large for the point-scatter kernel");
+  double *ddirs = nullptr, *dw = nullptr;
+  DirInfo *info = nullptr;
+  if (d.upload_doubles(dirs, ddirs) || d.upload_doubles(w, dw) || d.alloc(info, (size_t)P.shapes.s4[0] * w.size()))
+    return 1;
+  CUDA_TRY(launch_point_scatter_prepare(P, ddirs, (int)w.size(), info, g_stream));
+  SSource src = {a, b, ds_b ? P.medium.g[phase_component] : 0.0};
+  CUDA_TRY(launch_point_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], src, e, ddirs, dw, (int)w.size(), info, o,
+                                g_stream));
+  return d.download_rgb(o, n4, out);
+}
+
+extern "C" int atmlut_surface_radiance_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                             const atmlut_config *cfg, const float *ds_a, const float *ds_b,
+                                             int phase_component, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (!ds_a || !out) return fail("ds_a and out must not be NULL");
+  if (ds_b && (phase_component < 0 || phase_component >= n)) return fail("phase component out of range");
+  DevTables d;
+  const long long n4 = n4_of(P), ne = (long long)P.shapes.se[0] * P.shapes.se[1];
+  float4 *a = nullptr, *b = nullptr, *o = nullptr;
+  if (d.upload_rgb(ds_a, n4, a) || (ds_b && d.upload_rgb(ds_b, n4, b)) || d.alloc(o, (size_t)ne)) return 1;
+  std::vector<double> dirs, w;
+  sphere_directions(P.shapes.ray_steps >> 2, P.shapes.ray_steps, kPi / 2, dirs, w);
+  if (w.empty()) {
+    CUDA_TRY(cudaMemsetAsync(o, 0, (size_t)ne * sizeof(float4), g_stream));
+    return d.download_rgb(o, ne, out);
+  }
+  double *ddirs = nullptr, *dw = nullptr;
+  HalfDirInfo *info = nullptr;
+  if (d.upload_doubles(dirs, ddirs) || d.upload_doubles(w, dw) || d.alloc(info, (size_t)P.shapes.se[0] * w.size()))
+    return 1;
+  CUDA_TRY(launch_surface_radiance_prepare(P, ddirs, (int)w.size(), info, g_stream));
+  SSource src = {a, b, ds_b ? P.medium.g[phase_component] : 0.0};
+  CUDA_TRY(launch_surface_radiance(P, src, ddirs, dw, (int)w.size(), info, o, g_stream));
+  return d.download_rgb(o, ne, out);
+}
+
+extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                        const atmlut_config *cfg, const float *dj, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, scatter, n, cfg, P)) return 1;
+  if (!dj || !out) return fail("dj and out must not be NULL");
+  DevTables d;
+  const long long n4 = n4_of(P);
+  float4 *j = nullptr, *o = nullptr;
+  if (d.upload_rgb(dj, n4, j) || d.alloc(o, (size_t)n4)) return 1;
+  CUDA_TRY(launch_ray_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], j, o, nullptr, g_stream));
+  return d.download_rgb(o, n4, out);
+}
+
+extern "C" int atmlut_resample_table(const atmlut_planet *planet, const atmlut_config *cfg, int which,
+                                     const float *a, const float *b, float *out) {
+  Params P;
+  if (ensure_init() || make_params(planet, nullptr, 0, cfg, P)) return 1;
+  if (!out) return fail("out is NULL");
+  if (which < 0 || which > 2) return fail("which must be 0 (ray-scatter), 1 (surface-radiance) or 2 (transmittance)");
+  DevTables d;
+  const long long n = which == 0 ? n4_of(P)
+                                 : which == 1 ? (long long)P.shapes.se[0] * P.shapes.se[1]
+                                              : (long long)P.shapes.st[0] * P.shapes.st[1];
+  float4 *da = nullptr, *db = nullptr, *o = nullptr;
+  if ((a && d.upload_rgb(a, n, da)) || (b && d.upload_rgb(b, n, db)) || d.alloc(o, (size_t)n)) return 1;
+  if (which == 0)
+    CUDA_TRY(launch_resample_4d(P, 0, n, da, db, o, nullptr, g_stream));
+  else
+    CUDA_TRY(launch_resample_2d(P, which, da, db, o, nullptr, g_stream));
+  return d.download_rgb(o, n, out);
+}
+
+// ------------------------------------------------------------------ C ABI: output helpers
+
+// image.clj:299-312 convert-4d-to-2d
+extern "C" int atmlut_convert_4d_to_2d(const float *in, const int *shape, int ncomp, float *out) {
+  if (!in || !shape || !out || ncomp < 1) return fail("invalid argument");
+  const long long d = shape[0], c = shape[1], b = shape[2], a = shape[3];
+  const long long h = d * b, w = c * a;
+  for (long long y = 0; y < h; y++)
+    for (long long x = 0; x < w; x++) {
+      long long src = (((y / b) * c + (x / a)) * b + (y % b)) * a + (x % a);
+      for (int k = 0; k < ncomp; k++) out[(y * w + x) * ncomp + k] = in[src * ncomp + k];
+    }
+  return 0;
+}
+
+// util.clj:227-240 spit-floats: headerless little-endian float32
+extern "C" int atmlut_write_floats(const char *path, const float *data, long count) {
+  if (!path || (!data && count > 0)) return fail("invalid argument");
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(std::string("cannot open ") + path);
+  std::vector<unsigned char> buf((size_t)count * 4);
+  for (long i = 0; i < count; i++) {
+    unsigned int bits;
+    memcpy(&bits, &data[i], 4);
+    buf[4 * i] = (unsigned char)(bits & 255);
+    buf[4 * i + 1] = (unsigned char)((bits >> 8) & 255);
+    buf[4 * i + 2] = (unsigned char)((bits >> 16) & 255);
+    buf[4 * i + 3] = (unsigned char)((bits >> 24) & 255);
+  }
+  size_t written = fwrite(buf.data(), 1, buf.size(), f);
+  if (fclose(f) != 0 || written != buf.size()) return fail(std::string("short write to ") + path);
+  return 0;
+}
+
+// util.clj:188-203 slurp-floats
+extern "C" long atmlut_read_floats(const char *path, float *data, long max_count) {
+  if (!path || !data) return -1;
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  long n = 0;
+  unsigned char b[4];
+  while (n < max_count && fread(b, 1, 4, f) == 4) {
+    unsigned int bits = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+    memcpy(&data[n++], &bits, 4);
+  }
+  fclose(f);
+  return n;
+}

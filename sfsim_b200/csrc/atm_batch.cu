@@ -1,0 +1,439 @@
+// Batch point evaluators: the public functions of sfsim.atmosphere at arbitrary arguments, one
+// thread per item, in double precision on the device.  These are the entry points the host-side
+// mirror (sfsim_b200/atmosphere.py, or the Clojure shim) calls for single evaluations and for the
+// known-answer tests; the table kernels in atm_tables.cu are the throughput path.
+#include <vector>
+
+#include "atm_api_internal.h"
+#include "atm_math.cuh"
+
+namespace atm {
+
+namespace {
+
+__device__ __forceinline__ V3 load3(const double *p, int i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__device__ __forceinline__ void store3(double *p, int i, const double v[3]) {
+  p[3 * i] = v[0];
+  p[3 * i + 1] = v[1];
+  p[3 * i + 2] = v[2];
+}
+
+__global__ void k_transmittance_batch(Planet pl, Medium md, int steps, int count, const double *x, const double *x0,
+                                      double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double t[3];
+  transmittance_points(pl, md, steps, load3(x, i), load3(x0, i), t);
+  store3(out, i, t);
+}
+
+__global__ void k_transmittance_dir_batch(Planet pl, Medium md, int steps, int count, const double *x,
+                                          const double *v, const int *above, double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double t[3];
+  transmittance_dir(pl, md, steps, load3(x, i), load3(v, i), above[i] != 0, t);
+  store3(out, i, t);
+}
+
+// atmosphere.clj:131-137
+__global__ void k_surface_radiance_base_batch(Planet pl, Medium md, int steps, V3 intensity, int count,
+                                              const double *x, const double *l, double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  V3 xi = load3(x, i), li = load3(l, i);
+  double m = mag(xi);
+  V3 normal = v3(xi.x / m, xi.y / m, xi.z / m);
+  double t[3];
+  transmittance_dir(pl, md, steps, xi, li, true, t);
+  double f = fmax(0.0, dot(normal, li));
+  double r[3] = {(t[0] * intensity.x) * f, (t[1] * intensity.y) * f, (t[2] * intensity.z) * f};
+  store3(out, i, r);
+}
+
+// atmosphere.clj:140-189: kind 0 point-scatter-component, 1 strength-component, 2 point-scatter-base
+__device__ void point_scatter_first_order(const Planet &pl, const Medium &md, int kind, int component, int steps,
+                                          V3 intensity, V3 x, V3 v, V3 l, double out[3]) {
+  // filtered-sun-light (atmosphere.clj:154-160)
+  double sun[3] = {0.0, 0.0, 0.0};
+  if (is_above_horizon(pl, x, l)) {
+    double t[3];
+    transmittance_dir(pl, md, steps, x, l, true, t);
+    sun[0] = intensity.x * t[0];
+    sun[1] = intensity.y * t[1];
+    sun[2] = intensity.z * t[2];
+  }
+  const double h = height(pl, x);
+  const double mu = dot(v, l);
+  for (int ch = 0; ch < 3; ch++) {
+    double s;
+    if (kind == 1) {
+      s = scattering(md, component, ch, h);
+    } else if (kind == 0) {
+      s = scattering(md, component, ch, h) * phase(md.g[component], mu);
+    } else {
+      s = 0.0;
+      for (int c = 0; c < md.n; c++) {
+        double term = scattering(md, c, ch, h) * phase(md.g[c], mu);
+        s = (c == 0) ? term : s + term;
+      }
+    }
+    out[ch] = s * sun[ch];
+  }
+}
+
+__global__ void k_point_scatter_first_order_batch(Planet pl, Medium md, int kind, int component, int steps,
+                                                  V3 intensity, int count, const double *x, const double *v,
+                                                  const double *l, double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double r[3];
+  point_scatter_first_order(pl, md, kind, component, steps, intensity, load3(x, i), load3(v, i), load3(l, i), r);
+  store3(out, i, r);
+}
+
+// atmosphere.clj:192-200 ray-scatter with a first-order point-scatter function, plain restatement:
+// one warp per item, lanes over the outer samples
+__global__ void k_ray_scatter_first_order_batch(Planet pl, Medium md, int kind, int component, int steps,
+                                                V3 intensity, int count, const double *x, const double *v,
+                                                const double *l, const int *above, double *out) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= count) return;
+  V3 xi = load3(x, i), vi = load3(v, i), li = load3(l, i);
+  V3 point = above[i] ? atmosphere_intersection(pl, xi, vi) : surface_intersection(pl, xi, vi);
+  V3 d = point - xi;
+  double stepsize = 1.0 / (double)steps;
+  double a = stepsize * mag(d);
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int k = lane; k < steps; k += 32) {
+    double s = (0.5 + (double)k) * stepsize;
+    V3 p = xi + d * s;
+    double t[3], j[3];
+    transmittance_points(pl, md, steps, xi, p, t);
+    point_scatter_first_order(pl, md, kind, component, steps, intensity, p, vi, li, j);
+    for (int ch = 0; ch < 3; ch++) acc[ch] += (t[ch] * j[ch]) * a;
+  }
+  for (int ch = 0; ch < 3; ch++)
+    for (int o = 16; o > 0; o >>= 1) acc[ch] += __shfl_xor_sync(0xffffffffu, acc[ch], o);
+  if (lane == 0) store3(out, i, acc);
+}
+
+__global__ void k_index_forward(Planet pl, int which, int s0, int s1, int s2, int s3, int count,
+                                const double *point, const double *direction, const double *light, const int *above,
+                                double *indices) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int shape[4] = {s0, s1, s2, s3};
+  if (which == 0) {
+    double idx[4];
+    ray_scatter_forward(pl, shape, load3(point, i), load3(direction, i), load3(light, i), above[i] != 0, idx);
+    for (int k = 0; k < 4; k++) indices[4 * i + k] = idx[k];
+  } else if (which == 1) {
+    double idx[2];
+    surface_radiance_forward(pl, shape, load3(point, i), load3(light, i), idx);
+    indices[2 * i] = idx[0];
+    indices[2 * i + 1] = idx[1];
+  } else {
+    double idx[2];
+    transmittance_forward(pl, shape, load3(point, i), load3(direction, i), above[i] != 0, idx);
+    indices[2 * i] = idx[0];
+    indices[2 * i + 1] = idx[1];
+  }
+}
+
+__global__ void k_index_backward(Planet pl, int which, int s0, int s1, int s2, int s3, int count,
+                                 const double *indices, double *point, double *direction, double *light,
+                                 int *above) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int shape[4] = {s0, s1, s2, s3};
+  V3 p = v3(0, 0, 0), d = v3(0, 0, 0), l = v3(0, 0, 0);
+  bool ab = false;
+  if (which == 0)
+    ray_scatter_backward(pl, shape, indices[4 * i], indices[4 * i + 1], indices[4 * i + 2], indices[4 * i + 3], p, d,
+                         l, ab);
+  else if (which == 1)
+    surface_radiance_backward(pl, shape, indices[2 * i], indices[2 * i + 1], p, l);
+  else
+    transmittance_backward(pl, shape, indices[2 * i], indices[2 * i + 1], p, d, ab);
+  if (point) {
+    point[3 * i] = p.x;
+    point[3 * i + 1] = p.y;
+    point[3 * i + 2] = p.z;
+  }
+  if (direction) {
+    direction[3 * i] = d.x;
+    direction[3 * i + 1] = d.y;
+    direction[3 * i + 2] = d.z;
+  }
+  if (light) {
+    light[3 * i] = l.x;
+    light[3 * i + 1] = l.y;
+    light[3 * i + 2] = l.z;
+  }
+  if (above) above[i] = ab ? 1 : 0;
+}
+
+// interpolate.clj:87-98 interpolate-value, first axis outermost, mix = a (1 - s) + b s
+__global__ void k_interpolate(const float *table, int dims, int n0, int n1, int n2, int n3, int ncomp, int count,
+                              const double *coords, float *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int shape[4] = {n0, n1, n2, n3};
+  int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  float frac[4] = {0.f, 0.f, 0.f, 0.f};
+  long long stride[4];
+  long long s = ncomp;
+  for (int d = dims - 1; d >= 0; d--) {
+    stride[d] = s;
+    s *= shape[d];
+  }
+  for (int d = 0; d < dims; d++) {
+    double c = fmin(fmax(coords[(long long)i * dims + d], 0.0), (double)(shape[d] - 1));
+    double u = floor(c);
+    lo[d] = (int)u;
+    hi[d] = min(lo[d] + 1, shape[d] - 1);
+    frac[d] = (float)(c - u);
+  }
+  for (int k = 0; k < ncomp; k++) {
+    // evaluate the recursion bottom-up over the 2^dims corners
+    float vals[16];
+    const int corners = 1 << dims;
+    for (int c = 0; c < corners; c++) {
+      long long off = k;
+      for (int d = 0; d < dims; d++) off += (long long)(((c >> (dims - 1 - d)) & 1) ? hi[d] : lo[d]) * stride[d];
+      vals[c] = table[off];
+    }
+    for (int d = dims - 1; d >= 0; d--) {
+      const int half = 1 << d;
+      for (int c = 0; c < half; c++) vals[c] = vals[2 * c] * (1.0f - frac[d]) + vals[2 * c + 1] * frac[d];
+    }
+    out[(long long)i * ncomp + k] = vals[0];
+  }
+}
+
+struct Bufs {
+  std::vector<void *> ptrs;
+  ~Bufs() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  int up(const T *host, size_t count, T *&dev) {
+    dev = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dev, (count ? count : 1) * sizeof(T)));
+    ptrs.push_back(dev);
+    if (host && count)
+      CUDA_TRY(cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, stream()));
+    return 0;
+  }
+  template <typename T>
+  int down(const T *dev, size_t count, T *host) {
+    if (count) CUDA_TRY(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+    CUDA_TRY(cudaStreamSynchronize(stream()));
+    return 0;
+  }
+};
+
+// subtract the planet centre from an array of points
+std::vector<double> centred(const atmlut_planet *planet, const double *x, int count) {
+  std::vector<double> r((size_t)count * 3);
+  for (int i = 0; i < count; i++)
+    for (int k = 0; k < 3; k++) r[3 * i + k] = x[3 * i + k] - planet->centre[k];
+  return r;
+}
+
+int blocks(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+}  // namespace
+}  // namespace atm
+
+using namespace atm;
+
+#define CHECK_ARGS(cond, msg) \
+  do {                        \
+    if (!(cond)) return fail(msg); \
+  } while (0)
+
+extern "C" int atmlut_transmittance_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                                          int count, const double *x, const double *x0, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && x && x0 && out, "invalid argument");
+  if (count == 0) return 0;
+  Bufs b;
+  std::vector<double> cx = centred(planet, x, count), cx0 = centred(planet, x0, count);
+  double *dx, *dx0, *dout;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(cx0.data(), cx0.size(), dx0) || b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_transmittance_batch<<<blocks(count, 64), 64, 0, stream()>>>(P.planet, P.medium, steps, count, dx, dx0, dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_transmittance_dir_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                              int steps, int count, const double *x, const double *v,
+                                              const int *above, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && x && v && above && out, "invalid argument");
+  if (count == 0) return 0;
+  Bufs b;
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dv, *dout;
+  int *dab;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(v, (size_t)count * 3, dv) || b.up(above, (size_t)count, dab) ||
+      b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_transmittance_dir_batch<<<blocks(count, 64), 64, 0, stream()>>>(P.planet, P.medium, steps, count, dx, dv, dab,
+                                                                    dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_surface_radiance_base_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                                  int steps, const double *intensity, int count, const double *x,
+                                                  const double *l, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && intensity && x && l && out, "invalid argument");
+  if (count == 0) return 0;
+  Bufs b;
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dl, *dout;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(l, (size_t)count * 3, dl) || b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_surface_radiance_base_batch<<<blocks(count, 64), 64, 0, stream()>>>(
+      P.planet, P.medium, steps, v3(intensity[0], intensity[1], intensity[2]), count, dx, dl, dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_point_scatter_first_order_batch(const atmlut_planet *planet, const atmlut_scatter *scatter,
+                                                      int n, int kind, int component, int steps,
+                                                      const double *intensity, int count, const double *x,
+                                                      const double *v, const double *l, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && intensity && x && v && l && out, "invalid argument");
+  CHECK_ARGS(kind >= 0 && kind <= 2, "kind must be 0, 1 or 2");
+  CHECK_ARGS(kind == 2 || (component >= 0 && component < n), "component index out of range");
+  if (count == 0) return 0;
+  Bufs b;
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dv, *dl, *dout;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(v, (size_t)count * 3, dv) || b.up(l, (size_t)count * 3, dl) ||
+      b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_point_scatter_first_order_batch<<<blocks(count, 64), 64, 0, stream()>>>(
+      P.planet, P.medium, kind, component, steps, v3(intensity[0], intensity[1], intensity[2]), count, dx, dv, dl,
+      dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_ray_scatter_first_order_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                                    int kind, int component, int steps, const double *intensity,
+                                                    int count, const double *x, const double *v, const double *l,
+                                                    const int *above, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && intensity && x && v && l && above && out, "invalid argument");
+  CHECK_ARGS(kind >= 0 && kind <= 2, "kind must be 0, 1 or 2");
+  CHECK_ARGS(kind == 2 || (component >= 0 && component < n), "component index out of range");
+  if (count == 0) return 0;
+  Bufs b;
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dv, *dl, *dout;
+  int *dab;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(v, (size_t)count * 3, dv) || b.up(l, (size_t)count * 3, dl) ||
+      b.up(above, (size_t)count, dab) || b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_ray_scatter_first_order_batch<<<blocks((long long)count * 32, 128), 128, 0, stream()>>>(
+      P.planet, P.medium, kind, component, steps, v3(intensity[0], intensity[1], intensity[2]), count, dx, dv, dl, dab,
+      dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_index_forward_batch(const atmlut_planet *planet, int which, const int *shape, int count,
+                                          const double *point, const double *direction, const double *light,
+                                          const int *above, double *indices) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, nullptr, 0, P)) return 1;
+  CHECK_ARGS(which >= 0 && which <= 2 && shape && count >= 0 && point && indices, "invalid argument");
+  CHECK_ARGS(which == 1 || (direction && above), "direction and above are required for this space");
+  CHECK_ARGS(which == 2 || light, "light is required for this space");
+  if (count == 0) return 0;
+  const int dims = which == 0 ? 4 : 2;
+  int s[4] = {2, 2, 2, 2};
+  for (int i = 0; i < dims; i++) s[i] = shape[i];
+  Bufs b;
+  std::vector<double> cp = centred(planet, point, count);
+  double *dp, *dd = nullptr, *dl = nullptr, *didx;
+  int *dab = nullptr;
+  if (b.up(cp.data(), cp.size(), dp) || (direction && b.up(direction, (size_t)count * 3, dd)) ||
+      (light && b.up(light, (size_t)count * 3, dl)) || (above && b.up(above, (size_t)count, dab)) ||
+      b.up<double>(nullptr, (size_t)count * dims, didx))
+    return 1;
+  k_index_forward<<<blocks(count, 64), 64, 0, stream()>>>(P.planet, which, s[0], s[1], s[2], s[3], count, dp, dd, dl,
+                                                          dab, didx);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(didx, (size_t)count * dims, indices);
+}
+
+extern "C" int atmlut_index_backward_batch(const atmlut_planet *planet, int which, const int *shape, int count,
+                                           const double *indices, double *point, double *direction, double *light,
+                                           int *above) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, nullptr, 0, P)) return 1;
+  CHECK_ARGS(which >= 0 && which <= 2 && shape && count >= 0 && indices, "invalid argument");
+  if (count == 0) return 0;
+  const int dims = which == 0 ? 4 : 2;
+  int s[4] = {2, 2, 2, 2};
+  for (int i = 0; i < dims; i++) s[i] = shape[i];
+  Bufs b;
+  double *didx, *dp, *dd, *dl;
+  int *dab;
+  if (b.up(indices, (size_t)count * dims, didx) || b.up<double>(nullptr, (size_t)count * 3, dp) ||
+      b.up<double>(nullptr, (size_t)count * 3, dd) || b.up<double>(nullptr, (size_t)count * 3, dl) ||
+      b.up<int>(nullptr, (size_t)count, dab))
+    return 1;
+  k_index_backward<<<blocks(count, 64), 64, 0, stream()>>>(P.planet, which, s[0], s[1], s[2], s[3], count, didx, dp,
+                                                           dd, dl, dab);
+  CUDA_TRY(cudaGetLastError());
+  if (point) {
+    if (b.down(dp, (size_t)count * 3, point)) return 1;
+    for (int i = 0; i < count; i++)
+      for (int k = 0; k < 3; k++) point[3 * i + k] += planet->centre[k];
+  }
+  if (direction && b.down(dd, (size_t)count * 3, direction)) return 1;
+  if (light && b.down(dl, (size_t)count * 3, light)) return 1;
+  if (above && b.down(dab, (size_t)count, above)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(stream()));
+  return 0;
+}
+
+extern "C" int atmlut_interpolate_batch(const float *table, const int *shape, int dims, int ncomp, int count,
+                                        const double *coords, float *out) {
+  if (ensure_init()) return 1;
+  CHECK_ARGS(table && shape && coords && out && dims >= 1 && dims <= 4 && ncomp >= 1 && count >= 0,
+             "invalid argument");
+  if (count == 0) return 0;
+  int s[4] = {1, 1, 1, 1};
+  size_t total = ncomp;
+  for (int i = 0; i < dims; i++) {
+    CHECK_ARGS(shape[i] >= 1, "invalid shape");
+    s[i] = shape[i];
+    total *= (size_t)shape[i];
+  }
+  Bufs b;
+  float *dt, *dout;
+  double *dc;
+  if (b.up(table, total, dt) || b.up(coords, (size_t)count * dims, dc) ||
+      b.up<float>(nullptr, (size_t)count * ncomp, dout))
+    return 1;
+  k_interpolate<<<blocks(count, 64), 64, 0, stream()>>>(dt, dims, s[0], s[1], s[2], s[3], ncomp, count, dc, dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * ncomp, out);
+}

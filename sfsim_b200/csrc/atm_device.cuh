@@ -1,0 +1,220 @@
+// Device-side building blocks shared by the table kernels: the fast overall-extinction sampler
+// (FP64 position polynomial -> FP32 height polynomial -> MUFU.EX2), float4 table lookups, and the
+// parameter block every kernel receives.
+#pragma once
+
+#include "atm_math.cuh"
+
+namespace atm {
+
+constexpr int kMaxSteps = 256;       // ray_steps limit of the table kernels (shared-memory arrays)
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct Shapes {
+  int s4[4];  // height, elevation, light-elevation, heading
+  int st[2];  // transmittance height, elevation
+  int se[2];  // surface height, sun elevation
+  int ray_steps, sphere_steps;
+};
+
+// Constants of the fast sampler.  Heights are measured from R' = R - delta so that
+// r^2 - R'^2 stays strictly positive (its float image keeps full relative precision), and
+// h' = r - R' = h + delta is folded back into the exponent as an additive constant.
+struct Fast {
+  int poly;          // 1: (Rt^2 - R'^2) / R'^2 small enough for the series of sqrt(1+u) - 1
+  double rp2;        // R'^2
+  double inv_rp2;    // 1 / R'^2
+  float k[2];        // -R' * log2(e) / scale_c     (exponent slope in units of h'/R')
+  float b[2];        // delta * log2(e) / scale_c   (exponent offset)
+  float ext[2][3];   // extinction at h = 0: base_c / quotient_c
+};
+
+struct Params {
+  Planet planet;
+  Medium medium;
+  Shapes shapes;
+  Fast fast;
+  double intensity[3];
+};
+
+// float image of a positive normal double by truncation: two integer instructions instead of an
+// F2F.F32.F64 (which shares the 16/clk/SM conversion/SFU rate with MUFU.EX2, tools/pipe_peaks.cu).
+__device__ __forceinline__ float trunc_d2f(double d) {
+  int hi = __double2hiint(d), lo = __double2loint(d);
+  return __int_as_float(__funnelshift_l(lo, hi - 0x38000000, 3));
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp(-h/scale_c) for both components from u = (|q|^2 - R'^2) / R'^2  (fast path, u > 0 small)
+// sqrt(1+u) - 1 = u (1/2 - u/8 + u^2/16 - 5u^3/128 + 7u^4/256 - ...)
+__device__ __forceinline__ void densities_from_u(const Fast &f, float u, float &e0, float &e1) {
+  float q = fmaf(u, 0.02734375f, -0.0390625f);
+  q = fmaf(q, u, 0.0625f);
+  q = fmaf(q, u, -0.125f);
+  q = fmaf(q, u, 0.5f);
+  float hq = u * q;  // h' / R'
+  e0 = ex2_approx(fmaf(hq, f.k[0], f.b[0]));
+  e1 = ex2_approx(fmaf(hq, f.k[1], f.b[1]));
+}
+
+// Coefficients of u(m) = A + B m + C m^2, m = j + 1/2, for the samples q_j = o + dir (j + 1/2) / steps
+// given oo = |o|^2, od = o.dir, dd = |dir|^2.
+struct Quad {
+  double A, B, C;
+};
+
+__device__ __forceinline__ Quad make_quad(const Fast &f, double oo, double od, double dd, int steps) {
+  double inv = 1.0 / (double)steps;
+  Quad q;
+  q.A = (oo - f.rp2) * f.inv_rp2;
+  q.B = (2.0 * od * inv) * f.inv_rp2;
+  q.C = (dd * inv * inv) * f.inv_rp2;
+  return q;
+}
+
+// slow but general: exp(-h/scale) in double (planets whose atmosphere is not thin)
+__device__ __forceinline__ void densities_general(const Params &P, double rq2, float &e0, float &e1) {
+  double h = sqrt(rq2) - P.planet.radius;
+  e0 = (float)exp(-(h / P.medium.scale[0]));
+  e1 = (float)exp(-(h / P.medium.scale[1]));
+}
+
+// Sum over samples j = j0, j0 + stride, ... < steps of exp(-h(q_j)/scale_c).
+// Strided variant (used with one warp per segment): direct Horner evaluation per sample.
+__device__ __forceinline__ void density_sums_strided(const Params &P, const Quad &q, int steps, int j0, int stride,
+                                                     float &s0, float &s1, unsigned &count) {
+  s0 = 0.f;
+  s1 = 0.f;
+  for (int j = j0; j < steps; j += stride) {
+    double m = (double)j + 0.5;
+    double u = fma(fma(q.C, m, q.B), m, q.A);
+    float e0, e1;
+    if (P.fast.poly)
+      densities_from_u(P.fast, trunc_d2f(u), e0, e1);
+    else
+      densities_general(P, fma(u, P.fast.rp2, P.fast.rp2), e0, e1);
+    s0 += e0;
+    s1 += e1;
+    count++;
+  }
+}
+
+// Sequential variant (one thread per segment): forward differences in double (two DADD per
+// sample), four interleaved accumulators per component.
+__device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
+  if (P.fast.poly) {
+    double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // m = 1/2
+    double d1 = q.B + 2.0 * q.C;                     // u(m+1) - u(m) at m = 1/2
+    const double d2 = 2.0 * q.C;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, e0 = 0.f, e1 = 0.f;
+    int j = 0;
+    for (; j + 4 <= steps; j += 4) {
+      float x0, x1;
+      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+      a0 += x0; a1 += x1; u += d1; d1 += d2;
+      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+      b0 += x0; b1 += x1; u += d1; d1 += d2;
+      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+      c0 += x0; c1 += x1; u += d1; d1 += d2;
+      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+      e0 += x0; e1 += x1; u += d1; d1 += d2;
+    }
+    for (; j < steps; j++) {
+      float x0, x1;
+      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+      a0 += x0; a1 += x1; u += d1; d1 += d2;
+    }
+    s0 = (a0 + b0) + (c0 + e0);
+    s1 = (a1 + b1) + (c1 + e1);
+  } else {
+    s0 = 0.f;
+    s1 = 0.f;
+    for (int j = 0; j < steps; j++) {
+      double m = (double)j + 0.5;
+      double u = fma(fma(q.C, m, q.B), m, q.A);
+      float e0, e1;
+      densities_general(P, fma(u, P.fast.rp2, P.fast.rp2), e0, e1);
+      s0 += e0;
+      s1 += e1;
+    }
+  }
+}
+
+// exp(-(ext0 * c0 + ext1 * c1)) per colour channel, c = column densities (metres of sea-level medium)
+__device__ __forceinline__ void transmittance_rgb(const Fast &f, float c0, float c1, float t[3]) {
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    float tau = fmaf(f.ext[1][ch], c1, f.ext[0][ch] * c0);
+    t[ch] = ex2_approx(-tau * kLog2e);
+  }
+}
+
+// ------------------------------------------------------------------ float4 table lookups
+
+// interpolate.clj:75-98: clip to [0, n-1], u = floor, v = min(u + 1, n - 1), s = i - u
+struct Axis {
+  int u, v;
+  float s;
+};
+
+__device__ __forceinline__ Axis axis_from(float c, int n) {
+  float i = fminf(fmaxf(c, 0.0f), (float)(n - 1));
+  float u = floorf(i);
+  Axis a;
+  a.u = (int)u;
+  a.v = min(a.u + 1, n - 1);
+  a.s = i - u;
+  return a;
+}
+
+__device__ __forceinline__ Axis axis_from(double c, int n) {
+  double i = fmin(fmax(c, 0.0), (double)(n - 1));
+  double u = floor(i);
+  Axis a;
+  a.u = (int)u;
+  a.v = min(a.u + 1, n - 1);
+  a.s = (float)(i - u);
+  return a;
+}
+
+// interpolate.clj:81-84 mix: a (1 - s) + b s
+__device__ __forceinline__ float4 mix4(float4 a, float4 b, float s) {
+  float t = 1.0f - s;
+  return make_float4(fmaf(b.x, s, a.x * t), fmaf(b.y, s, a.y * t), fmaf(b.z, s, a.z * t), 0.0f);
+}
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// 4-D multilinear lookup, first axis outermost (interpolate.clj:87-98)
+__device__ __forceinline__ float4 lookup4(const float4 *__restrict__ tab, const int s4[4], Axis h, Axis e, Axis s,
+                                          Axis a) {
+  const int E = s4[1], S = s4[2], A = s4[3];
+  float4 he[2][2];
+#pragma unroll
+  for (int ih = 0; ih < 2; ih++) {
+#pragma unroll
+    for (int ie = 0; ie < 2; ie++) {
+      const float4 *base = tab + ((size_t)((ih ? h.v : h.u) * E + (ie ? e.v : e.u)) * S) * A;
+      const float4 *r0 = base + (size_t)s.u * A;
+      const float4 *r1 = base + (size_t)s.v * A;
+      float4 x0 = mix4(ldg4(r0 + a.u), ldg4(r0 + a.v), a.s);
+      float4 x1 = mix4(ldg4(r1 + a.u), ldg4(r1 + a.v), a.s);
+      he[ih][ie] = mix4(x0, x1, s.s);
+    }
+  }
+  return mix4(mix4(he[0][0], he[0][1], e.s), mix4(he[1][0], he[1][1], e.s), h.s);
+}
+
+// 2-D bilinear lookup
+__device__ __forceinline__ float4 lookup2(const float4 *__restrict__ tab, int cols, Axis r, Axis c) {
+  const float4 *r0 = tab + (size_t)r.u * cols;
+  const float4 *r1 = tab + (size_t)r.v * cols;
+  return mix4(mix4(ldg4(r0 + c.u), ldg4(r0 + c.v), c.s), mix4(ldg4(r1 + c.u), ldg4(r1 + c.v), c.s), r.s);
+}
+
+}  // namespace atm

@@ -1,0 +1,711 @@
+// Table kernels of the atmosphere-LUT build (one per reference loop nest) for sm_100a.
+//
+//   K1 k_transmittance_table        make-lookup-table of transmittance          (atmosphere.clj:114-128)
+//   K2 k_surface_radiance_base      make-lookup-table of surface-radiance-base  (atmosphere.clj:131-137)
+//   K3 k_first_order                ray-scatter of the first-order sources      (atmosphere.clj:170-200)
+//   K4 k_point_scatter              point-scatter (dJ)                          (atmosphere.clj:203-222)
+//   K5 k_surface_radiance           surface-radiance (dE)                       (atmosphere.clj:225-230)
+//   K6 k_ray_scatter                ray-scatter from the dJ table (dS)          (atmosphere.clj:192-200)
+//   K7 k_resample_*                 re-tabulation through forward o backward    (atmosphere_lut.clj:94-101)
+//
+// Sample positions are exactly the reference's.  What changes is who evaluates them: all inner
+// transmittance samples of one view ray lie on that ray, which is a function of the (height,
+// elevation) texel pair only, so one CTA owns one (height, elevation) pair, integrates the view
+// ray once into shared memory and then serves all (light-elevation, heading) texels from it.
+#include "atm_device.cuh"
+#include "atm_tables.h"
+
+namespace atm {
+
+// ------------------------------------------------------------------ view ray shared by one CTA
+
+struct ViewRay {
+  double r;        // |x|, x = (r, 0, 0)
+  double vx, vy;   // view direction (atmosphere.clj:256-270)
+  double dx, dy;   // ray end point minus x (atmosphere.clj:196-198)
+  double dlen;     // |d|
+  int above;
+};
+
+struct ViewSmem {
+  ViewRay ray;
+  double pkx[kMaxSteps], pky[kMaxSteps];  // outer sample points p_k
+  double rk2[kMaxSteps];                  // |p_k|^2
+  float cv0[kMaxSteps], cv1[kMaxSteps];   // column densities x -> p_k per component
+  float dens0[kMaxSteps], dens1[kMaxSteps];  // exp(-h(p_k)/scale_c)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Fills ViewSmem for texel pair (h, e) of the 4-D space: the view ray (ray-scatter-backward,
+// atmosphere.clj:401-412; ray end point :196-198), its `steps` outer sample points (ray.clj:19-30)
+// and the transmittance integral x -> p_k for every k (atmosphere.clj:118-125, :199).
+__device__ void setup_view_ray(const Params &P, int h, int e, ViewSmem &vs, unsigned &esamples) {
+  const int steps = P.shapes.ray_steps;
+  if (threadIdx.x == 0) {
+    V3 x = index_to_height(P.planet, P.shapes.s4[0], (double)h);
+    V3 v;
+    bool above;
+    index_to_elevation(P.planet, P.shapes.s4[1], x.x, (double)e, v, above);
+    V3 end = above ? atmosphere_intersection(P.planet, x, v) : surface_intersection(P.planet, x, v);
+    V3 d = end - x;
+    vs.ray.r = x.x;
+    vs.ray.vx = v.x;
+    vs.ray.vy = v.y;
+    vs.ray.dx = d.x;
+    vs.ray.dy = d.y;
+    vs.ray.dlen = mag(d);
+    vs.ray.above = above ? 1 : 0;
+  }
+  __syncthreads();
+  const ViewRay ray = vs.ray;
+  const double stepsize = 1.0 / (double)steps;
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    double s = (0.5 + (double)k) * stepsize;
+    double px = ray.r + ray.dx * s, py = ray.dy * s;
+    double r2 = px * px + py * py;
+    double hk = sqrt(r2) - P.planet.radius;
+    vs.pkx[k] = px;
+    vs.pky[k] = py;
+    vs.rk2[k] = r2;
+    vs.dens0[k] = (float)exp(-(hk / P.medium.scale[0]));
+    vs.dens1[k] = (float)exp(-(hk / P.medium.scale[1]));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int k = warp; k < steps; k += nwarps) {
+    // segment x -> p_k, direction d_k = p_k - x
+    double dkx = vs.pkx[k] - ray.r, dky = vs.pky[k];
+    double dd = dkx * dkx + dky * dky;
+    Quad q = make_quad(P.fast, ray.r * ray.r, ray.r * dkx, dd, steps);
+    float s0, s1;
+    density_sums_strided(P, q, steps, lane, 32, s0, s1, esamples);
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      double seg = stepsize * sqrt(dd);
+      vs.cv0[k] = (float)((double)s0 * seg);
+      vs.cv1[k] = (float)((double)s1 * seg);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void count_esamples(unsigned long long *counter, unsigned n) {
+  if (!counter) return;
+  n = (unsigned)__reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------ K1 / K2: 2-D tables in double
+
+// make-lookup-table of transmittance over transmittance-space (atmosphere_lut.clj:74)
+__global__ void k_transmittance_table(Params P, float4 *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = P.shapes.st[0] * P.shapes.st[1];
+  if (i >= n) return;
+  V3 x, v;
+  bool above;
+  transmittance_backward(P.planet, P.shapes.st, (double)(i / P.shapes.st[1]), (double)(i % P.shapes.st[1]), x, v,
+                         above);
+  double t[3];
+  transmittance_dir(P.planet, P.medium, P.shapes.ray_steps, x, v, above, t);
+  out[i] = make_float4((float)t[0], (float)t[1], (float)t[2], 0.0f);
+}
+
+// make-lookup-table of surface-radiance-base over surface-radiance-space (atmosphere_lut.clj:75)
+__global__ void k_surface_radiance_base(Params P, float4 *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = P.shapes.se[0] * P.shapes.se[1];
+  if (i >= n) return;
+  V3 x, l;
+  surface_radiance_backward(P.planet, P.shapes.se, (double)(i / P.shapes.se[1]), (double)(i % P.shapes.se[1]), x, l);
+  double t[3];
+  transmittance_dir(P.planet, P.medium, P.shapes.ray_steps, x, l, true, t);
+  double m = mag(x);
+  V3 normal = v3(x.x / m, x.y / m, x.z / m);
+  double f = fmax(0.0, dot(normal, l));
+  out[i] = make_float4((float)((t[0] * P.intensity[0]) * f), (float)((t[1] * P.intensity[1]) * f),
+                       (float)((t[2] * P.intensity[2]) * f), 0.0f);
+}
+
+// ------------------------------------------------------------------ K3: first-order ray scatter
+
+// One CTA per (height, elevation) pair, one thread per (light-elevation, heading) texel (optionally
+// split into `kparts` ranges of the outer sample index when the pair has few texels).
+// acc_c[ch] = sum_k exp(-h(p_k)/scale_c) T(x->p_k)[ch] T(p_k->sun)[ch] [sun visible from p_k]
+__global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int kparts, FirstOrderOut oa,
+                                                     FirstOrderOut ob, unsigned long long *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
+  float *partial = reinterpret_cast<float *>(smem_raw + sizeof(ViewSmem));  // [6][blockDim] when kparts > 1
+  const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const int he = he_begin + blockIdx.x;
+  const int h = he / E, e = he % E;
+  const int steps = P.shapes.ray_steps;
+  unsigned esamples = 0;
+  setup_view_ray(P, h, e, vs, esamples);
+  const ViewRay ray = vs.ray;
+  const int ntex = S * A;
+  const int items = ntex * kparts;
+  const double rt2 = sqr(P.planet.radius + P.planet.height);
+  const double r2 = sqr(P.planet.radius);
+  const double inv_steps = 1.0 / (double)steps;
+
+  for (int base = 0; base < items; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    const bool active = item < items;
+    const int texel = active ? item % ntex : 0;
+    const int part = active ? item / ntex : 0;
+    float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
+    V3 v = v3(ray.vx, ray.vy, 0.0);
+    V3 l = v3(0, 0, 0);
+    if (active) {
+      const int si = texel / A, ai = texel % A;
+      double ss = index_to_sin_sun_elevation(S, (double)si);
+      l = index_to_sun_direction(A, v, ss, (double)ai);
+      const double ll = dot(l, l);
+      const double llen = sqrt(ll);
+      const int k0 = (int)(((long long)steps * part) / kparts), k1 = (int)(((long long)steps * (part + 1)) / kparts);
+      for (int k = k0; k < k1; k++) {
+        const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
+        const double pl = l.x * pkx + l.y * pky;
+        // filtered-sun-light (atmosphere.clj:154-160): is-above-horizon? (p_k, l)
+        if (!(pl >= 0 || pl * pl <= rk2 - r2)) continue;
+        // atmosphere-intersection of (p_k, l) (atmosphere.clj:70-77, sphere.clj:46-59)
+        const double disc = pl * pl - ll * (rk2 - rt2);
+        const double middle = -(pl / ll);
+        double t;
+        if (disc > 0) {
+          double length2 = sqrt(disc) / ll;
+          t = (middle < length2) ? fmax(0.0, middle + length2) : (middle - length2) + 2 * length2;
+        } else {
+          t = fmax(0.0, middle);
+        }
+        // transmittance p_k -> end point: samples p_k + (l t)(j + 1/2)/steps
+        Quad q = make_quad(P.fast, rk2, pl * t, ll * t * t, steps);
+        float s0, s1;
+        density_sums_seq(P, q, steps, s0, s1);
+        esamples += steps;
+        const float seg = (float)(t * llen * inv_steps);
+        float tr[3];
+        transmittance_rgb(P.fast, fmaf(s0, seg, vs.cv0[k]), fmaf(s1, seg, vs.cv1[k]), tr);
+        const float d0 = vs.dens0[k], d1 = vs.dens1[k];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          acc0[ch] = fmaf(d0, tr[ch], acc0[ch]);
+          acc1[ch] = fmaf(d1, tr[ch], acc1[ch]);
+        }
+      }
+    }
+    if (kparts > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        partial[ch * blockDim.x + threadIdx.x] = acc0[ch];
+        partial[(3 + ch) * blockDim.x + threadIdx.x] = acc1[ch];
+      }
+      __syncthreads();
+      if (active && part == 0) {
+        for (int p = 1; p < kparts; p++) {
+          int other = p * ntex + texel - base;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            acc0[ch] += partial[ch * blockDim.x + other];
+            acc1[ch] += partial[(3 + ch) * blockDim.x + other];
+          }
+        }
+      }
+    }
+    if (active && part == 0) {
+      // ray.clj:19-30: every term carries a = stepsize * |direction|
+      const double a = inv_steps * ray.dlen;
+      const double mu = dot(v, l);
+      const size_t idx = (size_t)he * ntex + texel;
+      FirstOrderOut outs[2] = {oa, ob};
+#pragma unroll
+      for (int o = 0; o < 2; o++) {
+        if (!outs[o].table) continue;
+        const int c = outs[o].component;
+        const float *acc = c ? acc1 : acc0;
+        const double ph = outs[o].strength ? 1.0 : phase(P.medium.g[c], mu);
+        float4 val;
+        val.x = (float)(P.medium.base[c][0] * ph * P.intensity[0] * a * (double)acc[0]);
+        val.y = (float)(P.medium.base[c][1] * ph * P.intensity[1] * a * (double)acc[1]);
+        val.z = (float)(P.medium.base[c][2] * ph * P.intensity[2] * a * (double)acc[2]);
+        val.w = 0.0f;
+        outs[o].table[idx] = val;
+      }
+    }
+  }
+  count_esamples(counter, esamples);
+}
+
+// ------------------------------------------------------------------ K6: ray scatter from the dJ table
+
+struct LookupSmem {
+  int hu[kMaxSteps], hv[kMaxSteps], eu[kMaxSteps], ev[kMaxSteps];
+  float hs[kMaxSteps], es[kMaxSteps];
+  float tr[kMaxSteps][3];      // T(x -> p_k)
+  double inv_rk[kMaxSteps];    // 1 / |p_k|
+};
+
+// dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with
+// point-scatter = the interpolation-table of dJ, interpolate.clj:101-104)
+__global__ void __launch_bounds__(256) k_ray_scatter(Params P, int he_begin, const float4 *__restrict__ dj,
+                                                     float4 *out, unsigned long long *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
+  LookupSmem &ls = *reinterpret_cast<LookupSmem *>(smem_raw + sizeof(ViewSmem));
+  const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const int he = he_begin + blockIdx.x;
+  const int h = he / E, e = he % E;
+  const int steps = P.shapes.ray_steps;
+  unsigned esamples = 0;
+  setup_view_ray(P, h, e, vs, esamples);
+  const ViewRay ray = vs.ray;
+  const V3 v = v3(ray.vx, ray.vy, 0.0);
+  // per outer sample: lookup coordinates that do not depend on the light direction
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    V3 p = v3(vs.pkx[k], vs.pky[k], 0.0);
+    Axis ah = axis_from(height_to_index(P.planet, H, p), H);
+    Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
+    ls.hu[k] = ah.u;
+    ls.hv[k] = ah.v;
+    ls.hs[k] = ah.s;
+    ls.eu[k] = ae.u;
+    ls.ev[k] = ae.v;
+    ls.es[k] = ae.s;
+    float tr[3];
+    transmittance_rgb(P.fast, vs.cv0[k], vs.cv1[k], tr);
+    ls.tr[k][0] = tr[0];
+    ls.tr[k][1] = tr[1];
+    ls.tr[k][2] = tr[2];
+    ls.inv_rk[k] = 1.0 / sqrt(vs.rk2[k]);
+  }
+  __syncthreads();
+  const int ntex = S * A;
+  for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
+    const int si = texel / A, ai = texel % A;
+    double ss = index_to_sin_sun_elevation(S, (double)si);
+    V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+    const Axis aa = axis_from(sun_angle_to_index(A, v, l), A);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < steps; k++) {
+      const double pl = l.x * vs.pkx[k] + l.y * vs.pky[k];
+      // the sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
+      // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels
+      const Axis as = axis_from(sin_sun_elevation_to_index(S, pl * ls.inv_rk[k]), S);
+      Axis ah, ae;
+      ah.u = ls.hu[k];
+      ah.v = ls.hv[k];
+      ah.s = ls.hs[k];
+      ae.u = ls.eu[k];
+      ae.v = ls.ev[k];
+      ae.s = ls.es[k];
+      float4 j = lookup4(dj, P.shapes.s4, ah, ae, as, aa);
+      acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
+      acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
+      acc[2] = fmaf(ls.tr[k][2], j.z, acc[2]);
+    }
+    const float a = (float)(ray.dlen / (double)steps);
+    out[(size_t)he * ntex + texel] = make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f);
+  }
+  count_esamples(counter, esamples);
+}
+
+// ------------------------------------------------------------------ K4: point scatter
+
+// Per (height index, sphere direction): everything of in-scatter-from-direction
+// (atmosphere.clj:208-222) that does not depend on the view or light direction.
+__global__ void k_point_scatter_prepare(Params P, const double *__restrict__ dirs, int ndirs, DirInfo *info) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H = P.shapes.s4[0];
+  if (i >= H * ndirs) return;
+  const int h = i / ndirs, d = i % ndirs;
+  V3 x = index_to_height(P.planet, H, (double)h);
+  V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
+  V3 point = ray_extremity(P.planet, x, omega);
+  bool surface = surface_point(P.planet, point);
+  DirInfo r;
+  r.surface = surface ? 1 : 0;
+  Axis ae = axis_from(elevation_to_index(P.planet, P.shapes.s4[1], x, omega, !surface), P.shapes.s4[1]);
+  r.eu = ae.u;
+  r.ev = ae.v;
+  r.es = ae.s;
+  r.tb[0] = r.tb[1] = r.tb[2] = 0.f;
+  r.ehu = r.ehv = 0;
+  r.ehs = 0.f;
+  r.nx = r.ny = r.nz = 0.0;
+  if (surface) {
+    double t[3];
+    transmittance_points(P.planet, P.medium, P.shapes.ray_steps, x, point, t);
+    for (int ch = 0; ch < 3; ch++) r.tb[ch] = (float)(t[ch] * (P.planet.brightness[ch] / kPi));
+    Axis ah = axis_from(height_to_index(P.planet, P.shapes.se[0], point), P.shapes.se[0]);
+    r.ehu = ah.u;
+    r.ehv = ah.v;
+    r.ehs = ah.s;
+    double m = mag(point);
+    r.nx = point.x / m;
+    r.ny = point.y / m;
+    r.nz = point.z / m;
+  }
+  info[i] = r;
+}
+
+struct PointSmem {
+  float sc[kMaxDirs][3];   // weight_d * sum_c scattering_c(h(x)) phase_c(v . omega_d)
+};
+
+// dJ[i] = integral-sphere of overall-in-scattering * (S(x, omega, l, not surface) + surface term)
+__global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, SSource src,
+                                                       const float4 *__restrict__ de,
+                                                       const double *__restrict__ dirs,
+                                                       const double *__restrict__ weights, int ndirs,
+                                                       const DirInfo *__restrict__ info, float4 *out) {
+  __shared__ PointSmem ps;
+  __shared__ double s_geom[4];
+  const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const int he = he_begin + blockIdx.x;
+  const int h = he / E, e = he % E;
+  if (threadIdx.x == 0) {
+    V3 x = index_to_height(P.planet, H, (double)h);
+    V3 v;
+    bool above;
+    index_to_elevation(P.planet, E, x.x, (double)e, v, above);
+    s_geom[0] = x.x;
+    s_geom[1] = v.x;
+    s_geom[2] = v.y;
+  }
+  __syncthreads();
+  const V3 x = v3(s_geom[0], 0.0, 0.0);
+  const V3 v = v3(s_geom[1], s_geom[2], 0.0);
+  const double hx = height(P.planet, x);
+  for (int d = threadIdx.x; d < ndirs; d += blockDim.x) {
+    V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
+    double mu = dot(v, omega);
+    // overall-in-scattering (atmosphere.clj:147-151)
+    for (int ch = 0; ch < 3; ch++) {
+      double sum = 0.0;
+      for (int c = 0; c < P.medium.n; c++) {
+        double term = scattering(P.medium, c, ch, hx) * phase(P.medium.g[c], mu);
+        sum = (c == 0) ? term : sum + term;
+      }
+      ps.sc[d][ch] = (float)(sum * weights[d]);
+    }
+  }
+  __syncthreads();
+  const Axis ah = axis_from(height_to_index(P.planet, H, x), H);
+  const DirInfo *hinfo = info + (size_t)h * ndirs;
+  const int ntex = S * A;
+  for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
+    const int si = texel / A, ai = texel % A;
+    double ss = index_to_sin_sun_elevation(S, (double)si);
+    V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+    const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int d = 0; d < ndirs; d++) {
+      const DirInfo di = hinfo[d];
+      const double mu = dirs[3 * d] * l.x + dirs[3 * d + 1] * l.y + dirs[3 * d + 2] * l.z;
+      const Axis aa = axis_from((double)(A - 1) * ((1 + mu) / 2), A);
+      Axis ae;
+      ae.u = di.eu;
+      ae.v = di.ev;
+      ae.s = di.es;
+      float4 s = lookup4(src.tab_a, P.shapes.s4, ah, ae, as, aa);
+      if (src.tab_b) {
+        float4 m = lookup4(src.tab_b, P.shapes.s4, ah, ae, as, aa);
+        float ph = (float)phase(src.phase_g, mu);
+        s.x = fmaf(m.x, ph, s.x);
+        s.y = fmaf(m.y, ph, s.y);
+        s.z = fmaf(m.z, ph, s.z);
+      }
+      if (di.surface) {
+        // surface-radiance (point, l): interpolation-table of dE over surface-radiance-space
+        Axis eh;
+        eh.u = di.ehu;
+        eh.v = di.ehv;
+        eh.s = di.ehs;
+        double sin_elev = di.nx * l.x + di.ny * l.y + di.nz * l.z;
+        Axis es = axis_from(sin_sun_elevation_to_index(P.shapes.se[1], sin_elev), P.shapes.se[1]);
+        float4 ev = lookup2(de, P.shapes.se[1], eh, es);
+        s.x = fmaf(di.tb[0], ev.x, s.x);
+        s.y = fmaf(di.tb[1], ev.y, s.y);
+        s.z = fmaf(di.tb[2], ev.z, s.z);
+      }
+      acc[0] = fmaf(ps.sc[d][0], s.x, acc[0]);
+      acc[1] = fmaf(ps.sc[d][1], s.y, acc[1]);
+      acc[2] = fmaf(ps.sc[d][2], s.z, acc[2]);
+    }
+    out[(size_t)he * ntex + texel] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------ K5: surface radiance
+
+// per (surface height index, half-sphere direction): elevation coordinate of (x, omega, above = true)
+__global__ void k_surface_radiance_prepare(Params P, const double *__restrict__ dirs, int ndirs, HalfDirInfo *info) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.shapes.se[0] * ndirs) return;
+  const int h = i / ndirs, d = i % ndirs;
+  V3 x = index_to_height(P.planet, P.shapes.se[0], (double)h);
+  V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
+  Axis ae = axis_from(elevation_to_index(P.planet, P.shapes.s4[1], x, omega, true), P.shapes.s4[1]);
+  HalfDirInfo r;
+  r.eu = ae.u;
+  r.ev = ae.v;
+  r.es = ae.s;
+  info[i] = r;
+}
+
+// dE[i] = integral-half-sphere of S(x, omega, l, true) (omega . n)   (atmosphere.clj:225-230)
+__global__ void __launch_bounds__(256) k_surface_radiance(Params P, SSource src, const double *__restrict__ dirs,
+                                                          const double *__restrict__ weights, int ndirs,
+                                                          const HalfDirInfo *__restrict__ info, float4 *out) {
+  __shared__ float red[3][8];
+  const int i = blockIdx.x;
+  const int hi = i / P.shapes.se[1], si = i % P.shapes.se[1];
+  V3 x, l;
+  surface_radiance_backward(P.planet, P.shapes.se, (double)hi, (double)si, x, l);
+  const int H = P.shapes.s4[0], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const Axis ah = axis_from(height_to_index(P.planet, H, x), H);
+  const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
+  const double m = mag(x);
+  const V3 normal = v3(x.x / m, x.y / m, x.z / m);
+  const HalfDirInfo *hinfo = info + (size_t)hi * ndirs;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int d = threadIdx.x; d < ndirs; d += blockDim.x) {
+    V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
+    const double mu = dot(omega, l);
+    const Axis aa = axis_from((double)(A - 1) * ((1 + mu) / 2), A);
+    Axis ae;
+    ae.u = hinfo[d].eu;
+    ae.v = hinfo[d].ev;
+    ae.s = hinfo[d].es;
+    float4 s = lookup4(src.tab_a, P.shapes.s4, ah, ae, as, aa);
+    if (src.tab_b) {
+      float4 mm = lookup4(src.tab_b, P.shapes.s4, ah, ae, as, aa);
+      float ph = (float)phase(src.phase_g, mu);
+      s.x = fmaf(mm.x, ph, s.x);
+      s.y = fmaf(mm.y, ph, s.y);
+      s.z = fmaf(mm.z, ph, s.z);
+    }
+    const float f = (float)(dot(omega, normal) * weights[d]);
+    acc[0] = fmaf(s.x, f, acc[0]);
+    acc[1] = fmaf(s.y, f, acc[1]);
+    acc[2] = fmaf(s.z, f, acc[2]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ch = 0; ch < 3; ch++) {
+    float v = warp_sum(acc[ch]);
+    if (lane == 0) red[ch][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r[3];
+    for (int ch = 0; ch < 3; ch++) {
+      float v = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[ch][w];
+      r[ch] = v;
+    }
+    out[i] = make_float4(r[0], r[1], r[2], 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------ K7: re-tabulation
+
+// out[i] = lookup(a, g(i)) [+ lookup(b, g(i))], g = ray-scatter-forward o ray-scatter-backward.
+// file_layout != 0: write packed RGB float in convert-4d-to-2d order (image.clj:299-312).
+__global__ void k_resample_4d(Params P, long long begin, long long count, const float4 *__restrict__ a,
+                              const float4 *__restrict__ b, float4 *out, float *file_out) {
+  long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= begin + count) return;
+  const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const int ai = (int)(i % A), si = (int)((i / A) % S), ei = (int)((i / ((long long)A * S)) % E),
+            hi = (int)(i / ((long long)A * S * E));
+  V3 x, v, l;
+  bool above;
+  ray_scatter_backward(P.planet, P.shapes.s4, (double)hi, (double)ei, (double)si, (double)ai, x, v, l, above);
+  double idx[4];
+  ray_scatter_forward(P.planet, P.shapes.s4, x, v, l, above, idx);
+  const Axis ah = axis_from(idx[0], H), ae = axis_from(idx[1], E), as = axis_from(idx[2], S), aa = axis_from(idx[3], A);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a) r = lookup4(a, P.shapes.s4, ah, ae, as, aa);
+  if (b) {
+    float4 t = lookup4(b, P.shapes.s4, ah, ae, as, aa);
+    r.x += t.x;
+    r.y += t.y;
+    r.z += t.z;
+  }
+  if (out) out[i] = r;
+  if (file_out) {
+    const long long y = (long long)hi * S + si, xx = (long long)ei * A + ai;
+    float *o = file_out + (y * ((long long)E * A) + xx) * 3;
+    o[0] = r.x;
+    o[1] = r.y;
+    o[2] = r.z;
+  }
+}
+
+// which = 1: surface-radiance-space, which = 2: transmittance-space
+__global__ void k_resample_2d(Params P, int which, const float4 *__restrict__ a, const float4 *__restrict__ b,
+                              float4 *out, float *file_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int *shape = which == 1 ? P.shapes.se : P.shapes.st;
+  if (i >= shape[0] * shape[1]) return;
+  double idx[2];
+  if (which == 1) {
+    V3 x, l;
+    surface_radiance_backward(P.planet, shape, (double)(i / shape[1]), (double)(i % shape[1]), x, l);
+    surface_radiance_forward(P.planet, shape, x, l, idx);
+  } else {
+    V3 x, v;
+    bool above;
+    transmittance_backward(P.planet, shape, (double)(i / shape[1]), (double)(i % shape[1]), x, v, above);
+    transmittance_forward(P.planet, shape, x, v, above, idx);
+  }
+  const Axis ar = axis_from(idx[0], shape[0]), ac = axis_from(idx[1], shape[1]);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a) r = lookup2(a, shape[1], ar, ac);
+  if (b) {
+    float4 t = lookup2(b, shape[1], ar, ac);
+    r.x += t.x;
+    r.y += t.y;
+    r.z += t.z;
+  }
+  if (out) out[i] = r;
+  if (file_out) {
+    file_out[3 * i] = r.x;
+    file_out[3 * i + 1] = r.y;
+    file_out[3 * i + 2] = r.z;
+  }
+}
+
+// RGB float <-> padded float4 conversion for the host-facing table entry points
+__global__ void k_rgb_to_float4(const float *in, float4 *out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.f);
+}
+
+__global__ void k_float4_to_rgb(const float4 *in, float *out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float4 v = in[i];
+    out[3 * i] = v.x;
+    out[3 * i + 1] = v.y;
+    out[3 * i + 2] = v.z;
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+
+static int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
+
+cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_t st) {
+  int n = P.shapes.st[0] * P.shapes.st[1];
+  k_transmittance_table<<<div_up(n, 64), 64, 0, st>>>(P, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st) {
+  int n = P.shapes.se[0] * P.shapes.se[1];
+  k_surface_radiance_base<<<div_up(n, 64), 64, 0, st>>>(P, out);
+  return cudaGetLastError();
+}
+
+static int first_order_kparts(const Params &P, int threads) {
+  int ntex = P.shapes.s4[2] * P.shapes.s4[3];
+  if (ntex >= threads) return 1;
+  int kp = threads / ntex;
+  return kp < P.shapes.ray_steps ? kp : P.shapes.ray_steps;
+}
+
+cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, FirstOrderOut oa, FirstOrderOut ob,
+                               unsigned long long *counter, cudaStream_t st) {
+  if (he_count <= 0) return cudaSuccess;
+  const int threads = 256;
+  int kparts = first_order_kparts(P, threads);
+  size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_first_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ViewSmem) + 6 * 256 * 4));
+    attr = true;
+  }
+  k_first_order<<<he_count, threads, smem, st>>>(P, he_begin, kparts, oa, ob, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, const float4 *dj, float4 *out,
+                               unsigned long long *counter, cudaStream_t st) {
+  if (he_count <= 0) return cudaSuccess;
+  size_t smem = sizeof(ViewSmem) + sizeof(LookupSmem);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  k_ray_scatter<<<he_count, 256, smem, st>>>(P, he_begin, dj, out, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
+                                         cudaStream_t st) {
+  int n = P.shapes.s4[0] * ndirs;
+  k_point_scatter_prepare<<<div_up(n, 64), 64, 0, st>>>(P, dirs, ndirs, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, SSource src, const float4 *de,
+                                 const double *dirs, const double *weights, int ndirs, const DirInfo *info,
+                                 float4 *out, cudaStream_t st) {
+  if (he_count <= 0) return cudaSuccess;
+  k_point_scatter<<<he_count, 256, 0, st>>>(P, he_begin, src, de, dirs, weights, ndirs, info, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,
+                                            cudaStream_t st) {
+  int n = P.shapes.se[0] * ndirs;
+  k_surface_radiance_prepare<<<div_up(n, 128), 128, 0, st>>>(P, dirs, ndirs, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *dirs, const double *weights,
+                                    int ndirs, const HalfDirInfo *info, float4 *out, cudaStream_t st) {
+  int n = P.shapes.se[0] * P.shapes.se[1];
+  k_surface_radiance<<<n, 256, 0, st>>>(P, src, dirs, weights, ndirs, info, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_4d(const Params &P, long long begin, long long count, const float4 *a, const float4 *b,
+                               float4 *out, float *file_out, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  k_resample_4d<<<div_up(count, 128), 128, 0, st>>>(P, begin, count, a, b, out, file_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_2d(const Params &P, int which, const float4 *a, const float4 *b, float4 *out,
+                               float *file_out, cudaStream_t st) {
+  const int *shape = which == 1 ? P.shapes.se : P.shapes.st;
+  int n = shape[0] * shape[1];
+  k_resample_2d<<<div_up(n, 128), 128, 0, st>>>(P, which, a, b, out, file_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rgb_to_float4(const float *in, float4 *out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_rgb_to_float4<<<div_up(n, 256), 256, 0, st>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_float4_to_rgb(const float4 *in, float *out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_float4_to_rgb<<<div_up(n, 256), 256, 0, st>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace atm

@@ -1,0 +1,66 @@
+// Host-visible declarations of the table kernels' launchers (atm_tables.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "atm_device.cuh"
+
+namespace atm {
+
+constexpr int kMaxDirs = 2048;  // sphere quadrature directions the point-scatter kernel keeps in shared memory
+
+// one output of the first-order kernel: ray-scatter of point-scatter-component (strength = 0) or
+// strength-component (strength = 1) of scatter[component]
+struct FirstOrderOut {
+  float4 *table;
+  int component;
+  int strength;
+};
+
+// S source of point-scatter / surface-radiance: tab_a, or tab_a + tab_b * phase(phase_g, v.l)
+// (the closure of atmosphere_lut.clj:79-84)
+struct SSource {
+  const float4 *tab_a;
+  const float4 *tab_b;
+  double phase_g;
+};
+
+// per (height index, sphere direction) constants of in-scatter-from-direction (atmosphere.clj:208-222)
+struct DirInfo {
+  int surface;        // surface-point? of the ray extremity
+  int eu, ev;         // elevation axis corners of S(x, omega, l, not surface)
+  float es;
+  float tb[3];        // T(x -> point) * brightness / pi
+  int ehu, ehv;       // height axis corners of E(point, l)
+  float ehs;
+  double nx, ny, nz;  // point / |point|
+};
+
+struct HalfDirInfo {
+  int eu, ev;
+  float es;
+};
+
+cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_t st);
+cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st);
+cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, FirstOrderOut oa, FirstOrderOut ob,
+                               unsigned long long *counter, cudaStream_t st);
+cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, const float4 *dj, float4 *out,
+                               unsigned long long *counter, cudaStream_t st);
+cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
+                                         cudaStream_t st);
+cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, SSource src, const float4 *de,
+                                 const double *dirs, const double *weights, int ndirs, const DirInfo *info,
+                                 float4 *out, cudaStream_t st);
+cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,
+                                            cudaStream_t st);
+cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *dirs, const double *weights,
+                                    int ndirs, const HalfDirInfo *info, float4 *out, cudaStream_t st);
+cudaError_t launch_resample_4d(const Params &P, long long begin, long long count, const float4 *a, const float4 *b,
+                               float4 *out, float *file_out, cudaStream_t st);
+cudaError_t launch_resample_2d(const Params &P, int which, const float4 *a, const float4 *b, float4 *out,
+                               float *file_out, cudaStream_t st);
+cudaError_t launch_rgb_to_float4(const float *in, float4 *out, long long n, cudaStream_t st);
+cudaError_t launch_float4_to_rgb(const float4 *in, float *out, long long n, cudaStream_t st);
+
+}  // namespace atm
