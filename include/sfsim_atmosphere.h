@@ -54,6 +54,7 @@ typedef struct {
 /* ---- lifetime (jolt_init / jolt_destroy, jolt.cc:137-182) ---- */
 int atmlut_init(int device);                 /* select the CUDA device, create the stream */
 void atmlut_destroy(void);
+void *atmlut_stream(void);                   /* the library's cudaStream_t (for timing / ordering by the host) */
 const char *atmlut_last_error(void);
 int atmlut_device_count(void);
 void atmlut_default_config(atmlut_config *cfg); /* shipped constants, atmosphere_lut.clj:47-63 */
@@ -76,6 +77,9 @@ int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter *scatter, 
 typedef int (*atmlut_allgather_fn)(void *user, void *device_buf, size_t bytes_per_rank, void *stream);
 int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
                           const atmlut_config *cfg, int rank, int world, void **builder);
+/* the partition: rank owns (height, elevation) pairs [begin, begin + count) of n_pairs = height_size *
+ * elevation_size, padded to per_rank pairs per rank (host-only helper, needs no device) */
+int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank);
 int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *user);
 int atmlut_builder_run(void *builder);        /* asynchronous on the library stream */
 int atmlut_builder_sync(void *builder);       /* wait for the stream */
@@ -87,6 +91,9 @@ const char *atmlut_builder_stage_name(void *builder, int stage);
 int atmlut_builder_stage_ms(void *builder, int stage, float *ms);
 /* sample counts of the last run: overall-extinction evaluations, 4-D lookups, 2-D lookups */
 int atmlut_builder_work(void *builder, double *esamples, double *lookups4d, double *lookups2d);
+/* which: 0 = overall-extinction samples of the first-order kernel, 1 = of the ray-scatter kernels (all
+ * iterations), both counted on the device for this rank's slab; 2 = kernels launched by the last run */
+int atmlut_builder_counter(void *builder, int which, double *value);
 int atmlut_builder_destroy(void *builder);
 
 /* ---- per-table entry points: make-lookup-table of each public function over its space ----
@@ -149,6 +156,19 @@ int atmlut_index_forward_batch(const atmlut_planet *planet, int which, const int
                                double *indices);
 int atmlut_index_backward_batch(const atmlut_planet *planet, int which, const int *shape, int count,
                                 const double *indices, double *point, double *direction, double *light, int *above);
+
+/* the scalar maps one by one; a, b are double[3] per item, out is double[3] per item (unused lanes 0):
+ *   fn 0 elevation-to-index   (a = point, b = direction, flag = above-horizon)        -> out[0]     :239-253
+ *   fn 1 index-to-elevation   (a = (radius, index, -))                                -> out = direction, out_flag = above :256-270
+ *   fn 2 height-to-index      (a = point)                                             -> out[0]     :273-278
+ *   fn 3 index-to-height      (a = (index, -, -))                                     -> out = point :281-288
+ *   fn 4 sun-elevation-to-index (a = point, b = light)                                -> out[0]     :322-326
+ *   fn 5 index-to-sin-sun-elevation (a = (index, -, -))                               -> out[0]     :329-332
+ *   fn 6 sun-angle-to-index   (a = direction, b = light)                              -> out[0]     :368-372
+ *   fn 7 index-to-sun-direction (a = direction, b = (sin sun elevation, index, -))    -> out = light :375-384
+ *   fn 8 horizon-distance     (a = (radius, -, -))                                    -> out[0]     :233-236 */
+int atmlut_index_map_batch(const atmlut_planet *planet, int fn, int size, int count, const double *a,
+                           const double *b, const int *flag, double *out, int *out_flag);
 
 /* interpolate-value (interpolate.clj:87-98) on a float table of `ncomp`-vectors, dims <= 4 */
 int atmlut_interpolate_batch(const float *table, const int *shape, int dims, int ncomp, int count,

@@ -207,7 +207,7 @@ static void spherical_integral(long theta_steps, long phi_steps, double theta_ra
   double delta2 = theta_range / (double)theta_steps / 2;
   double mat[9];
   orc_oriented_matrix(normal, mat);
-  double acc[8], ring[8];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ring[8]; /* (reduce add []) of zero rings: the reference throws; we return 0 */
   for (long k = 0; k < theta_steps; k++) {
     double theta = theta_range * ((0.5 + (double)k) / (double)theta_steps);
     double factor = cos(theta - delta2) - cos(theta + delta2);

@@ -54,17 +54,18 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 
 # every symbol include/sfsim_atmosphere.h declares
 EXPORTS = [
-    "atmlut_init", "atmlut_destroy", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
+    "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate",
-    "atmlut_builder_create", "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
+    "atmlut_builder_create", "atmlut_slab", "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
     "atmlut_builder_download", "atmlut_builder_stage_count", "atmlut_builder_stage_name", "atmlut_builder_stage_ms",
-    "atmlut_builder_work", "atmlut_builder_destroy",
+    "atmlut_builder_work", "atmlut_builder_counter", "atmlut_builder_destroy",
     "atmlut_transmittance_table", "atmlut_surface_radiance_base_table", "atmlut_first_order_tables",
     "atmlut_point_scatter_table", "atmlut_surface_radiance_table", "atmlut_ray_scatter_table",
     "atmlut_resample_table",
     "atmlut_transmittance_batch", "atmlut_transmittance_dir_batch", "atmlut_surface_radiance_base_batch",
     "atmlut_point_scatter_first_order_batch", "atmlut_ray_scatter_first_order_batch",
-    "atmlut_index_forward_batch", "atmlut_index_backward_batch", "atmlut_interpolate_batch",
+    "atmlut_index_forward_batch", "atmlut_index_backward_batch", "atmlut_index_map_batch",
+    "atmlut_interpolate_batch",
     "atmlut_convert_4d_to_2d", "atmlut_write_floats", "atmlut_read_floats",
 ]
 
@@ -83,6 +84,7 @@ def load():
         lib.atmlut_builder_stage_name.restype = C.c_char_p
         lib.atmlut_builder_stage_name.argtypes = [C.c_void_p, C.c_int]
         lib.atmlut_read_floats.restype = C.c_long
+        lib.atmlut_stream.restype = C.c_void_p
         lib.atmlut_builder_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                               C.POINTER(C.c_void_p)]
         for name in ("atmlut_builder_set_allgather",):
@@ -93,6 +95,7 @@ def load():
         lib.atmlut_builder_download.argtypes = [C.c_void_p] * 5
         lib.atmlut_builder_stage_ms.argtypes = [C.c_void_p, C.c_int, c_float_p]
         lib.atmlut_builder_work.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+        lib.atmlut_builder_counter.argtypes = [C.c_void_p, C.c_int, c_double_p]
         _lib = lib
     return _lib
 

@@ -142,7 +142,12 @@ class AtmosphereLutBuilder:
     def work(self):
         e, l4, l2 = C.c_double(), C.c_double(), C.c_double()
         check(self.lib.atmlut_builder_work(self.handle, C.byref(e), C.byref(l4), C.byref(l2)))
-        return {"esamples": e.value, "lookups4d": l4.value, "lookups2d": l2.value}
+        res = {"esamples": e.value, "lookups4d": l4.value, "lookups2d": l2.value}
+        for which, key in enumerate(("esamples_first_order", "esamples_ray_scatter", "kernel_launches")):
+            v = C.c_double()
+            check(self.lib.atmlut_builder_counter(self.handle, which, C.byref(v)))
+            res[key] = v.value
+        return res
 
     def close(self):
         if self.handle:

@@ -154,6 +154,7 @@ struct Builder {
   size_t stage_cursor = 0;
   bool ran = false;
   double esamples = 0, lookups4d = 0, lookups2d = 0;
+  long long launches = 0;   // kernels launched by the last run
 
   ~Builder() {
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dJ, S, S_new, file_T, file_E, file_S, file_M,
@@ -180,13 +181,19 @@ static int upload(double *&dst, const std::vector<double> &src) {
   return 0;
 }
 
+// Slab of rank `rank`: (height, elevation) pairs [begin, begin + count); every rank owns `per_rank` slots
+// of the (padded) table so that one equal-sized all-gather reassembles it.
+static void slab_of(int n_pairs, int rank, int world, int &begin, int &count, int &per_rank) {
+  per_rank = (n_pairs + world - 1) / world;
+  begin = rank * per_rank;
+  count = std::max(0, std::min(n_pairs, begin + per_rank) - begin);
+}
+
 static int builder_alloc(Builder &b) {
   const Params &P = b.P;
   b.n_he = P.shapes.s4[0] * P.shapes.s4[1];
   b.ntex = (long long)P.shapes.s4[2] * P.shapes.s4[3];
-  b.he_per_rank = (b.n_he + b.world - 1) / b.world;
-  b.he_begin = b.rank * b.he_per_rank;
-  b.he_count = std::max(0, std::min(b.n_he, b.he_begin + b.he_per_rank) - b.he_begin);
+  slab_of(b.n_he, b.rank, b.world, b.he_begin, b.he_count, b.he_per_rank);
   b.n4 = b.n_he * b.ntex;
   b.n4_pad = (long long)b.he_per_rank * b.world * b.ntex;
   b.nt = (long long)P.shapes.st[0] * P.shapes.st[1];
@@ -248,13 +255,18 @@ static int gather(Builder &b, float4 *table) {
   do {                     \
     if (expr) return 1;    \
   } while (0)
-#define LAUNCH(expr) CUDA_TRY(expr)
+#define LAUNCH(expr) \
+  do {               \
+    CUDA_TRY(expr);   \
+    b.launches++;     \
+  } while (0)
 
 // generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below)
 static int builder_run(Builder &b) {
   const Params &P = b.P;
   cudaStream_t st = g_stream;
   b.stage_cursor = 0;
+  b.launches = 0;
   CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
   const long long slab_begin = (long long)b.he_begin * b.ntex, slab_count = (long long)b.he_count * b.ntex;
   (void)slab_begin;
@@ -356,7 +368,14 @@ extern "C" int atmlut_init(int device) {
   return 0;
 }
 
+namespace {
+void drop_generate_cache();
+}
+
+extern "C" void *atmlut_stream(void) { return (void *)g_stream; }
+
 extern "C" void atmlut_destroy(void) {
+  drop_generate_cache();
   if (g_stream) {
     cudaStreamSynchronize(g_stream);
     cudaStreamDestroy(g_stream);
@@ -409,6 +428,13 @@ extern "C" int atmlut_builder_create(const atmlut_planet *planet, const atmlut_s
     return 1;
   }
   *builder = b;
+  return 0;
+}
+
+extern "C" int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank) {
+  if (n_pairs < 0 || world < 1 || rank < 0 || rank >= world || !begin || !count || !per_rank)
+    return fail("invalid argument");
+  slab_of(n_pairs, rank, world, *begin, *count, *per_rank);
   return 0;
 }
 
@@ -494,6 +520,21 @@ extern "C" int atmlut_builder_work(void *builder, double *esamples, double *look
   return 0;
 }
 
+extern "C" int atmlut_builder_counter(void *builder, int which, double *value) {
+  Builder *b = (Builder *)builder;
+  if (!b || !b->ran || !value) return fail("builder has not run");
+  if (which == 2) {
+    *value = (double)b->launches;
+    return 0;
+  }
+  if (which < 0 || which > 2) return fail("which must be 0, 1 or 2");
+  unsigned long long c[2];
+  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, g_stream));
+  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  *value = (double)c[which];
+  return 0;
+}
+
 extern "C" int atmlut_builder_destroy(void *builder) {
   if (!builder) return 0;
   cudaStreamSynchronize(g_stream);
@@ -501,14 +542,43 @@ extern "C" int atmlut_builder_destroy(void *builder) {
   return 0;
 }
 
+// The one-shot call keeps its builder (device tables, quadrature tables, events) between calls with
+// identical parameters, so a repeated build pays for kernels and the result copy only.
+namespace {
+struct GenerateCache {
+  void *builder = nullptr;
+  atmlut_planet planet;
+  atmlut_scatter scatter[2];
+  atmlut_config cfg;
+  int device = -1;
+} g_cache;
+
+void drop_generate_cache() {
+  if (g_cache.builder) atmlut_builder_destroy(g_cache.builder);
+  g_cache.builder = nullptr;
+}
+}  // namespace
+
 extern "C" int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
                                const atmlut_config *cfg, float *transmittance, float *surface_radiance,
                                float *ray_scatter, float *mie_strength) {
-  void *b = nullptr;
-  if (atmlut_builder_create(planet, scatter, n, cfg, 0, 1, &b)) return 1;
-  int rc = atmlut_builder_run(b);
-  if (!rc) rc = atmlut_builder_download(b, transmittance, surface_radiance, ray_scatter, mie_strength);
-  atmlut_builder_destroy(b);
+  if (ensure_init()) return 1;
+  if (!planet || !scatter || !cfg) return fail("planet, scatter and config must not be NULL");
+  if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
+  const bool hit = g_cache.builder && g_cache.device == g_device && !memcmp(&g_cache.planet, planet, sizeof *planet) &&
+                   !memcmp(g_cache.scatter, scatter, 2 * sizeof *scatter) && !memcmp(&g_cache.cfg, cfg, sizeof *cfg);
+  if (!hit) {
+    drop_generate_cache();
+    if (atmlut_builder_create(planet, scatter, n, cfg, 0, 1, &g_cache.builder)) return 1;
+    g_cache.planet = *planet;
+    g_cache.scatter[0] = scatter[0];
+    g_cache.scatter[1] = scatter[1];
+    g_cache.cfg = *cfg;
+    g_cache.device = g_device;
+  }
+  int rc = atmlut_builder_run(g_cache.builder);
+  if (!rc) rc = atmlut_builder_download(g_cache.builder, transmittance, surface_radiance, ray_scatter, mie_strength);
+  if (rc) drop_generate_cache();
   return rc;
 }
 

@@ -175,6 +175,31 @@ __global__ void k_index_backward(Planet pl, int which, int s0, int s1, int s2, i
   if (above) above[i] = ab ? 1 : 0;
 }
 
+// the scalar index maps of atmosphere.clj:233-384, one item per thread (fn codes in sfsim_atmosphere.h)
+__global__ void k_index_map(Planet pl, int fn, int size, int count, const double *a, const double *b, const int *flag,
+                            double *out, int *out_flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  V3 va = a ? load3(a, i) : v3(0, 0, 0), vb = b ? load3(b, i) : v3(0, 0, 0);
+  V3 r = v3(0, 0, 0);
+  bool ab = false;
+  switch (fn) {
+    case 0: r.x = elevation_to_index(pl, size, va, vb, flag[i] != 0); break;
+    case 1: index_to_elevation(pl, size, va.x, va.y, r, ab); break;
+    case 2: r.x = height_to_index(pl, size, va); break;
+    case 3: r = index_to_height(pl, size, va.x); break;
+    case 4: r.x = sun_elevation_to_index(size, va, vb); break;
+    case 5: r.x = index_to_sin_sun_elevation(size, va.x); break;
+    case 6: r.x = sun_angle_to_index(size, va, vb); break;
+    case 7: r = index_to_sun_direction(size, va, vb.x, vb.y); break;
+    default: r.x = horizon_distance(pl, va.x); break;
+  }
+  out[3 * i] = r.x;
+  out[3 * i + 1] = r.y;
+  out[3 * i + 2] = r.z;
+  if (out_flag) out_flag[i] = ab ? 1 : 0;
+}
+
 // interpolate.clj:87-98 interpolate-value, first axis outermost, mix = a (1 - s) + b s
 __global__ void k_interpolate(const float *table, int dims, int n0, int n1, int n2, int n3, int ncomp, int count,
                               const double *coords, float *out) {
@@ -411,6 +436,35 @@ extern "C" int atmlut_index_backward_batch(const atmlut_planet *planet, int whic
   if (light && b.down(dl, (size_t)count * 3, light)) return 1;
   if (above && b.down(dab, (size_t)count, above)) return 1;
   CUDA_TRY(cudaStreamSynchronize(stream()));
+  return 0;
+}
+
+extern "C" int atmlut_index_map_batch(const atmlut_planet *planet, int fn, int size, int count, const double *a,
+                                      const double *b, const int *flag, double *out, int *out_flag) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, nullptr, 0, P)) return 1;
+  CHECK_ARGS(fn >= 0 && fn <= 8 && count >= 0 && a && out, "invalid argument");
+  CHECK_ARGS(fn != 0 || flag, "elevation-to-index needs the above-horizon flags");
+  CHECK_ARGS(!(fn == 0 || fn == 4 || fn == 6 || fn == 7) || b, "this map needs a second argument");
+  CHECK_ARGS(fn == 8 || fn == 4 || fn == 6 || size >= 2 || fn == 5, "size must be at least 2");
+  if (count == 0) return 0;
+  Bufs bufs;
+  std::vector<double> ca;
+  const bool point_arg = (fn == 0 || fn == 2 || fn == 4);
+  if (point_arg) ca = centred(planet, a, count);
+  double *da, *db = nullptr, *dout;
+  int *dflag = nullptr, *doflag = nullptr;
+  if (bufs.up(point_arg ? ca.data() : a, (size_t)count * 3, da) || (b && bufs.up(b, (size_t)count * 3, db)) ||
+      (flag && bufs.up(flag, (size_t)count, dflag)) || bufs.up<double>(nullptr, (size_t)count * 3, dout) ||
+      bufs.up<int>(nullptr, (size_t)count, doflag))
+    return 1;
+  k_index_map<<<blocks(count, 64), 64, 0, stream()>>>(P.planet, fn, size, count, da, db, dflag, dout, doflag);
+  CUDA_TRY(cudaGetLastError());
+  if (bufs.down(dout, (size_t)count * 3, out)) return 1;
+  if (fn == 3)
+    for (int i = 0; i < count; i++)
+      for (int k = 0; k < 3; k++) out[3 * i + k] += planet->centre[k];
+  if (out_flag && bufs.down(doflag, (size_t)count, out_flag)) return 1;
   return 0;
 }
 
