@@ -251,7 +251,7 @@ struct LookupSmem {
   int hu[kMaxSteps], hv[kMaxSteps], eu[kMaxSteps], ev[kMaxSteps];
   float hs[kMaxSteps], es[kMaxSteps];
   float tr[kMaxSteps][3];      // T(x -> p_k)
-  double inv_rk[kMaxSteps];    // 1 / |p_k|
+  double rk[kMaxSteps];        // |p_k|
 };
 
 // dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_ray_scatter(Params P, int he_begin, con
     ls.tr[k][0] = tr[0];
     ls.tr[k][1] = tr[1];
     ls.tr[k][2] = tr[2];
-    ls.inv_rk[k] = 1.0 / sqrt(vs.rk2[k]);
+    ls.rk[k] = sqrt(vs.rk2[k]);
   }
   __syncthreads();
   const int ntex = S * A;
@@ -298,8 +298,10 @@ __global__ void __launch_bounds__(256) k_ray_scatter(Params P, int he_begin, con
     for (int k = 0; k < steps; k++) {
       const double pl = l.x * vs.pkx[k] + l.y * vs.pky[k];
       // the sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
-      // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels
-      const Axis as = axis_from(sin_sun_elevation_to_index(S, pl * ls.inv_rk[k]), S);
+      // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.  The
+      // true division keeps it bit-identical to the reference's (dot p l) / (mag p), so that rows the
+      // reference clamps to exactly 0 are clamped here as well.
+      const Axis as = axis_from(sin_sun_elevation_to_index(S, pl / ls.rk[k]), S);
       Axis ah, ae;
       ah.u = ls.hu[k];
       ah.v = ls.hv[k];
@@ -341,6 +343,7 @@ __global__ void k_point_scatter_prepare(Params P, const double *__restrict__ dir
   r.ehu = r.ehv = 0;
   r.ehs = 0.f;
   r.nx = r.ny = r.nz = 0.0;
+  r.nmag = 1.0;
   if (surface) {
     double t[3];
     transmittance_points(P.planet, P.medium, P.shapes.ray_steps, x, point, t);
@@ -349,10 +352,10 @@ __global__ void k_point_scatter_prepare(Params P, const double *__restrict__ dir
     r.ehu = ah.u;
     r.ehv = ah.v;
     r.ehs = ah.s;
-    double m = mag(point);
-    r.nx = point.x / m;
-    r.ny = point.y / m;
-    r.nz = point.z / m;
+    r.nx = point.x;
+    r.ny = point.y;
+    r.nz = point.z;
+    r.nmag = mag(point);
   }
   info[i] = r;
 }
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, S
         eh.u = di.ehu;
         eh.v = di.ehv;
         eh.s = di.ehs;
-        double sin_elev = di.nx * l.x + di.ny * l.y + di.nz * l.z;
+        double sin_elev = (di.nx * l.x + di.ny * l.y + di.nz * l.z) / di.nmag;
         Axis es = axis_from(sin_sun_elevation_to_index(P.shapes.se[1], sin_elev), P.shapes.se[1]);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
         s.x = fmaf(di.tb[0], ev.x, s.x);

@@ -33,7 +33,8 @@ struct DirInfo {
   float tb[3];        // T(x -> point) * brightness / pi
   int ehu, ehv;       // height axis corners of E(point, l)
   float ehs;
-  double nx, ny, nz;  // point / |point|
+  double nx, ny, nz;  // the ray extremity `point` ...
+  double nmag;        // ... and |point|
 };
 
 struct HalfDirInfo {

@@ -353,9 +353,12 @@ def test_shipped_build_properties(shipped):
     # energy: every order adds light, and orders decay -> total S is between first order and a small multiple
     assert 0.2 < float(s.max()) < 1.0
     H, E, S, A = cfg.ray_scatter_shape
-    # sun far below the horizon (light-elevation index 0 <-> sin = -0.2): no single scattering anywhere
+    # on the ground every below-horizon view ray has length zero (surface-intersection distance 0), and the
+    # re-tabulation maps that half row onto its own middle texel: exactly no light
     m4 = m.reshape(H, S, E, A, 3)
-    assert float(np.abs(m4[:, 0]).max()) < 1e-12
+    assert float(np.abs(m4[0, :, :E // 2 + 1]).max()) == 0.0
+    assert float(np.abs(s.reshape(H, S, E, A, 3)[0, :, :E // 2 + 1]).max()) == 0.0
+    assert float(m4[0, S - 1, E // 2 + 1:].min()) > 0.0
     # blue scatters more than red looking up from the ground with the sun at the zenith
     s4 = s.reshape(H, S, E, A, 3)
     assert np.all(s4[0, S - 1, E // 2 + 1, :, 2] > s4[0, S - 1, E // 2 + 1, :, 0])
