@@ -89,6 +89,8 @@ int make_params(const atmlut_planet *planet, const atmlut_scatter *scatter, int 
     if (sizes[i] < 2) return fail("every table axis needs at least 2 entries");
   if (cfg->ray_steps < 1 || cfg->ray_steps > kMaxSteps) return fail("ray_steps must be in [1, 256]");
   if (cfg->sphere_steps < 2) return fail("sphere_steps must be at least 2");
+  if ((long long)cfg->light_elevation_size * cfg->heading_size > 6144)
+    return fail("light_elevation_size * heading_size must not exceed 6144 (shared-memory tile of the ray-scatter kernel)");
   for (int i = 0; i < 4; i++) P.shapes.s4[i] = sizes[i];
   P.shapes.st[0] = sizes[4];
   P.shapes.st[1] = sizes[5];
@@ -148,6 +150,7 @@ struct Builder {
   double *sphere_dirs = nullptr, *sphere_w = nullptr, *half_dirs = nullptr, *half_w = nullptr;
   int n_sphere = 0, n_half = 0;
   DirInfo *dir_info = nullptr;
+  float4 *tiles_a = nullptr, *tiles_b = nullptr;   // blended S tiles per (height, sphere direction)
   HalfDirInfo *half_info = nullptr;
   unsigned long long *counter = nullptr;
   std::vector<Stage> stages;
@@ -158,7 +161,8 @@ struct Builder {
 
   ~Builder() {
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dJ, S, S_new, file_T, file_E, file_S, file_M,
-                    sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter};
+                    sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
+                    tiles_a, tiles_b};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     for (auto &s : stages) {
@@ -222,6 +226,8 @@ static int builder_alloc(Builder &b) {
   b.n_half = (int)w.size();
   if (b.n_half > 0 && (upload(b.half_dirs, dirs) || upload(b.half_w, w))) return 1;
   if (dev_alloc(b.dir_info, (size_t)P.shapes.s4[0] * b.n_sphere)) return 1;
+  if (dev_alloc(b.tiles_a, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
+  if (dev_alloc(b.tiles_b, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
   if (dev_alloc(b.half_info, (size_t)P.shapes.se[0] * std::max(1, b.n_half))) return 1;
   return 0;
 }
@@ -296,8 +302,10 @@ static int builder_run(Builder &b) {
     char name[64];
     snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
     TRY(stage_begin(b, name));
-    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, ds, b.dE, b.sphere_dirs, b.sphere_w, b.n_sphere,
-                                b.dir_info, b.dJ, st));                              // :88,90
+    LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, b.tiles_a, st));
+    if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, b.tiles_b, st));
+    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g, b.dE,
+                                b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.dJ, st));  // :88,90
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_point_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
@@ -693,8 +701,13 @@ extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atm
   if (d.upload_doubles(dirs, ddirs) || d.upload_doubles(w, dw) || d.alloc(info, (size_t)P.shapes.s4[0] * w.size()))
     return 1;
   CUDA_TRY(launch_point_scatter_prepare(P, ddirs, (int)w.size(), info, g_stream));
-  SSource src = {a, b, ds_b ? P.medium.g[phase_component] : 0.0};
-  CUDA_TRY(launch_point_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], src, e, ddirs, dw, (int)w.size(), info, o,
+  float4 *ta = nullptr, *tb = nullptr;
+  const size_t tile_count = (size_t)P.shapes.s4[0] * w.size() * P.shapes.s4[2] * P.shapes.s4[3];
+  if (d.alloc(ta, tile_count) || (b && d.alloc(tb, tile_count))) return 1;
+  CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), ta, g_stream));
+  if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), tb, g_stream));
+  CUDA_TRY(launch_point_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
+                                ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info, o,
                                 g_stream));
   return d.download_rgb(o, n4, out);
 }

@@ -210,6 +210,13 @@ __device__ __forceinline__ float4 lookup4(const float4 *__restrict__ tab, const 
   return mix4(mix4(he[0][0], he[0][1], e.s), mix4(he[1][0], he[1][1], e.s), h.s);
 }
 
+// 2-D bilinear lookup in a shared-memory tile
+__device__ __forceinline__ float4 lookup2_smem(const float4 *tab, int cols, Axis r, Axis c) {
+  const float4 *r0 = tab + r.u * cols;
+  const float4 *r1 = tab + r.v * cols;
+  return mix4(mix4(r0[c.u], r0[c.v], c.s), mix4(r1[c.u], r1[c.v], c.s), r.s);
+}
+
 // 2-D bilinear lookup
 __device__ __forceinline__ float4 lookup2(const float4 *__restrict__ tab, int cols, Axis r, Axis c) {
   const float4 *r0 = tab + (size_t)r.u * cols;

@@ -27,7 +27,7 @@ struct ViewRay {
   int above;
 };
 
-struct ViewSmem {
+struct alignas(16) ViewSmem {
   ViewRay ray;
   double pkx[kMaxSteps], pky[kMaxSteps];  // outer sample points p_k
   double rk2[kMaxSteps];                  // |p_k|^2
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int
 
 // ------------------------------------------------------------------ K6: ray scatter from the dJ table
 
-struct LookupSmem {
+struct alignas(16) LookupSmem {
   int hu[kMaxSteps], hv[kMaxSteps], eu[kMaxSteps], ev[kMaxSteps];
   float hs[kMaxSteps], es[kMaxSteps];
   float tr[kMaxSteps][3];      // T(x -> p_k)
@@ -255,12 +255,19 @@ struct LookupSmem {
 };
 
 // dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with
-// point-scatter = the interpolation-table of dJ, interpolate.clj:101-104)
-__global__ void __launch_bounds__(256) k_ray_scatter(Params P, int he_begin, const float4 *__restrict__ dj,
-                                                     float4 *out, unsigned long long *counter) {
+// point-scatter = the interpolation-table of dJ, interpolate.clj:101-104).
+//
+// All texels of the CTA look dJ up at the same height and elevation coordinates for a given outer
+// sample k (they depend on p_k and v only), so the CTA first blends the four (height, elevation)
+// corner tiles of dJ into one [light-elevation][heading] tile in shared memory (coalesced float4
+// loads, double buffered), and each texel then interpolates inside that tile: 4 shared-memory loads
+// per lookup instead of 16 scattered global ones.
+__global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, const float4 *__restrict__ dj,
+                                                      float4 *out, unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
   LookupSmem &ls = *reinterpret_cast<LookupSmem *>(smem_raw + sizeof(ViewSmem));
+  float4 *tiles = reinterpret_cast<float4 *>(smem_raw + sizeof(ViewSmem) + sizeof(LookupSmem));
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int he = he_begin + blockIdx.x;
   const int h = he / E, e = he % E;
@@ -289,33 +296,41 @@ __global__ void __launch_bounds__(256) k_ray_scatter(Params P, int he_begin, con
   }
   __syncthreads();
   const int ntex = S * A;
-  for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
-    const int si = texel / A, ai = texel % A;
-    double ss = index_to_sin_sun_elevation(S, (double)si);
-    V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+  const float a = (float)(ray.dlen / (double)steps);
+  for (int chunk = 0; chunk < ntex; chunk += blockDim.x) {
+    const int texel = chunk + threadIdx.x;
+    const bool active = texel < ntex;
+    const int si = active ? texel / A : 0, ai = active ? texel % A : 0;
+    const double ss = index_to_sin_sun_elevation(S, (double)si);
+    const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
     const Axis aa = axis_from(sun_angle_to_index(A, v, l), A);
     float acc[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < steps; k++) {
-      const double pl = l.x * vs.pkx[k] + l.y * vs.pky[k];
-      // the sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
-      // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.  The
-      // true division keeps it bit-identical to the reference's (dot p l) / (mag p), so that rows the
-      // reference clamps to exactly 0 are clamped here as well.
-      const Axis as = axis_from(sin_sun_elevation_to_index(S, pl / ls.rk[k]), S);
-      Axis ah, ae;
-      ah.u = ls.hu[k];
-      ah.v = ls.hv[k];
-      ah.s = ls.hs[k];
-      ae.u = ls.eu[k];
-      ae.v = ls.ev[k];
-      ae.s = ls.es[k];
-      float4 j = lookup4(dj, P.shapes.s4, ah, ae, as, aa);
-      acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
-      acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
-      acc[2] = fmaf(ls.tr[k][2], j.z, acc[2]);
+      float4 *tile = tiles + (size_t)(k & 1) * ntex;
+      {
+        const size_t r00 = ((size_t)ls.hu[k] * E + ls.eu[k]) * ntex, r01 = ((size_t)ls.hu[k] * E + ls.ev[k]) * ntex;
+        const size_t r10 = ((size_t)ls.hv[k] * E + ls.eu[k]) * ntex, r11 = ((size_t)ls.hv[k] * E + ls.ev[k]) * ntex;
+        const float es = ls.es[k], hs = ls.hs[k];
+        for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
+          tile[idx] = mix4(mix4(ldg4(dj + r00 + idx), ldg4(dj + r01 + idx), es),
+                           mix4(ldg4(dj + r10 + idx), ldg4(dj + r11 + idx), es), hs);
+      }
+      __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
+      if (active) {
+        const double pl = l.x * vs.pkx[k] + l.y * vs.pky[k];
+        // the sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
+        // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.  The
+        // true division keeps it bit-identical to the reference's (dot p l) / (mag p), so that rows the
+        // reference clamps to exactly 0 are clamped here as well.
+        const Axis as = axis_from(sin_sun_elevation_to_index(S, pl / ls.rk[k]), S);
+        const float4 j = lookup2_smem(tile, A, as, aa);
+        acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
+        acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
+        acc[2] = fmaf(ls.tr[k][2], j.z, acc[2]);
+      }
     }
-    const float a = (float)(ray.dlen / (double)steps);
-    out[(size_t)he * ntex + texel] = make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f);
+    if (active) out[(size_t)he * ntex + texel] = make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f);
+    __syncthreads();
   }
   count_esamples(counter, esamples);
 }
@@ -360,17 +375,47 @@ __global__ void k_point_scatter_prepare(Params P, const double *__restrict__ dir
   info[i] = r;
 }
 
-struct PointSmem {
-  float sc[kMaxDirs][3];   // weight_d * sum_c scattering_c(h(x)) phase_c(v . omega_d)
+// S(x, omega_d, l, not surface) is looked up at height and elevation coordinates that depend on the
+// height index h and the direction d only (atmosphere.clj:217: point x = (r_h, 0, 0), direction omega_d),
+// never on the view or light direction.  Blend those two axes once per (h, d):
+// tiles[(h * ndirs + d)][s][a] = mix_h(mix_e(tab)); the point-scatter kernel then interpolates the two
+// remaining axes inside one 4 KB tile (4 loads per lookup instead of 16, shared by 127 CTAs).
+__global__ void __launch_bounds__(256) k_blend_dir_tiles(Params P, const float4 *__restrict__ tab,
+                                                         const DirInfo *__restrict__ info, int ndirs, float4 *tiles) {
+  const int H = P.shapes.s4[0], E = P.shapes.s4[1];
+  const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
+  const int hd = blockIdx.x;
+  const int h = hd / ndirs;
+  const V3 x = index_to_height(P.planet, H, (double)h);
+  const Axis ah = axis_from(height_to_index(P.planet, H, x), H);
+  const DirInfo di = info[hd];
+  const size_t r00 = ((size_t)ah.u * E + di.eu) * ntex, r01 = ((size_t)ah.u * E + di.ev) * ntex;
+  const size_t r10 = ((size_t)ah.v * E + di.eu) * ntex, r11 = ((size_t)ah.v * E + di.ev) * ntex;
+  float4 *tile = tiles + (size_t)hd * ntex;
+  for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
+    tile[idx] = mix4(mix4(ldg4(tab + r00 + idx), ldg4(tab + r01 + idx), di.es),
+                     mix4(ldg4(tab + r10 + idx), ldg4(tab + r11 + idx), di.es), ah.s);
+}
+
+struct alignas(16) PointDir {
+  double ox, oy, oz;      // omega_d
+  double px, py, pz, pm;  // ray extremity and its norm (surface directions)
+  float sc[3];            // weight_d * sum_c scattering_c(h(x)) phase_c(v . omega_d)
+  float tb[3];            // T(x -> point) * brightness / pi
+  int surface;
+  int ehu, ehv;
+  float ehs;
 };
 
 // dJ[i] = integral-sphere of overall-in-scattering * (S(x, omega, l, not surface) + surface term)
-__global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, SSource src,
+__global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, const float4 *__restrict__ tiles_a,
+                                                       const float4 *__restrict__ tiles_b, double phase_g,
                                                        const float4 *__restrict__ de,
                                                        const double *__restrict__ dirs,
                                                        const double *__restrict__ weights, int ndirs,
                                                        const DirInfo *__restrict__ info, float4 *out) {
-  __shared__ PointSmem ps;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PointDir *pd = reinterpret_cast<PointDir *>(smem_raw);
   __shared__ double s_geom[4];
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int he = he_begin + blockIdx.x;
@@ -391,6 +436,10 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, S
   for (int d = threadIdx.x; d < ndirs; d += blockDim.x) {
     V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
     double mu = dot(v, omega);
+    PointDir r;
+    r.ox = omega.x;
+    r.oy = omega.y;
+    r.oz = omega.z;
     // overall-in-scattering (atmosphere.clj:147-151)
     for (int ch = 0; ch < 3; ch++) {
       double sum = 0.0;
@@ -398,13 +447,25 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, S
         double term = scattering(P.medium, c, ch, hx) * phase(P.medium.g[c], mu);
         sum = (c == 0) ? term : sum + term;
       }
-      ps.sc[d][ch] = (float)(sum * weights[d]);
+      r.sc[ch] = (float)(sum * weights[d]);
     }
+    const DirInfo di = info[(size_t)h * ndirs + d];
+    r.surface = di.surface;
+    r.tb[0] = di.tb[0];
+    r.tb[1] = di.tb[1];
+    r.tb[2] = di.tb[2];
+    r.ehu = di.ehu;
+    r.ehv = di.ehv;
+    r.ehs = di.ehs;
+    r.px = di.nx;
+    r.py = di.ny;
+    r.pz = di.nz;
+    r.pm = di.nmag;
+    pd[d] = r;
   }
   __syncthreads();
-  const Axis ah = axis_from(height_to_index(P.planet, H, x), H);
-  const DirInfo *hinfo = info + (size_t)h * ndirs;
   const int ntex = S * A;
+  const size_t tile_base = (size_t)h * ndirs * ntex;
   for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
     const int si = texel / A, ai = texel % A;
     double ss = index_to_sin_sun_elevation(S, (double)si);
@@ -412,37 +473,33 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, S
     const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
     float acc[3] = {0.f, 0.f, 0.f};
     for (int d = 0; d < ndirs; d++) {
-      const DirInfo di = hinfo[d];
-      const double mu = dirs[3 * d] * l.x + dirs[3 * d + 1] * l.y + dirs[3 * d + 2] * l.z;
+      const PointDir &r = pd[d];
+      const double mu = r.ox * l.x + r.oy * l.y + r.oz * l.z;
       const Axis aa = axis_from((double)(A - 1) * ((1 + mu) / 2), A);
-      Axis ae;
-      ae.u = di.eu;
-      ae.v = di.ev;
-      ae.s = di.es;
-      float4 s = lookup4(src.tab_a, P.shapes.s4, ah, ae, as, aa);
-      if (src.tab_b) {
-        float4 m = lookup4(src.tab_b, P.shapes.s4, ah, ae, as, aa);
-        float ph = (float)phase(src.phase_g, mu);
+      float4 s = lookup2(tiles_a + tile_base + (size_t)d * ntex, A, as, aa);
+      if (tiles_b) {
+        float4 m = lookup2(tiles_b + tile_base + (size_t)d * ntex, A, as, aa);
+        float ph = (float)phase(phase_g, mu);
         s.x = fmaf(m.x, ph, s.x);
         s.y = fmaf(m.y, ph, s.y);
         s.z = fmaf(m.z, ph, s.z);
       }
-      if (di.surface) {
+      if (r.surface) {
         // surface-radiance (point, l): interpolation-table of dE over surface-radiance-space
         Axis eh;
-        eh.u = di.ehu;
-        eh.v = di.ehv;
-        eh.s = di.ehs;
-        double sin_elev = (di.nx * l.x + di.ny * l.y + di.nz * l.z) / di.nmag;
+        eh.u = r.ehu;
+        eh.v = r.ehv;
+        eh.s = r.ehs;
+        double sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
         Axis es = axis_from(sin_sun_elevation_to_index(P.shapes.se[1], sin_elev), P.shapes.se[1]);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
-        s.x = fmaf(di.tb[0], ev.x, s.x);
-        s.y = fmaf(di.tb[1], ev.y, s.y);
-        s.z = fmaf(di.tb[2], ev.z, s.z);
+        s.x = fmaf(r.tb[0], ev.x, s.x);
+        s.y = fmaf(r.tb[1], ev.y, s.y);
+        s.z = fmaf(r.tb[2], ev.z, s.z);
       }
-      acc[0] = fmaf(ps.sc[d][0], s.x, acc[0]);
-      acc[1] = fmaf(ps.sc[d][1], s.y, acc[1]);
-      acc[2] = fmaf(ps.sc[d][2], s.z, acc[2]);
+      acc[0] = fmaf(r.sc[0], s.x, acc[0]);
+      acc[1] = fmaf(r.sc[1], s.y, acc[1]);
+      acc[2] = fmaf(r.sc[2], s.z, acc[2]);
     }
     out[(size_t)he * ntex + texel] = make_float4(acc[0], acc[1], acc[2], 0.0f);
   }
@@ -642,16 +699,24 @@ cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, Firs
   return cudaGetLastError();
 }
 
+static int ray_scatter_threads(const Params &P) {
+  int ntex = P.shapes.s4[2] * P.shapes.s4[3];
+  int t = (ntex + 31) / 32 * 32;
+  return t < 128 ? 128 : (t > 1024 ? 1024 : t);
+}
+
+size_t ray_scatter_smem(const Params &P) {
+  return sizeof(ViewSmem) + sizeof(LookupSmem) + 2 * (size_t)P.shapes.s4[2] * P.shapes.s4[3] * sizeof(float4);
+}
+
 cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, const float4 *dj, float4 *out,
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
-  size_t smem = sizeof(ViewSmem) + sizeof(LookupSmem);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  k_ray_scatter<<<he_count, 256, smem, st>>>(P, he_begin, dj, out, counter);
+  size_t smem = ray_scatter_smem(P);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // light-elevation x heading tile too large
+  cudaError_t e = cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, he_begin, dj, out, counter);
   return cudaGetLastError();
 }
 
@@ -662,11 +727,22 @@ cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, in
   return cudaGetLastError();
 }
 
-cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, SSource src, const float4 *de,
-                                 const double *dirs, const double *weights, int ndirs, const DirInfo *info,
-                                 float4 *out, cudaStream_t st) {
+cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, float4 *tiles,
+                                   cudaStream_t st) {
+  k_blend_dir_tiles<<<P.shapes.s4[0] * ndirs, 256, 0, st>>>(P, tab, info, ndirs, tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, const float4 *tiles_a,
+                                 const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
+                                 const double *weights, int ndirs, const DirInfo *info, float4 *out,
+                                 cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
-  k_point_scatter<<<he_count, 256, 0, st>>>(P, he_begin, src, de, dirs, weights, ndirs, info, out);
+  size_t smem = (size_t)ndirs * sizeof(PointDir);
+  cudaError_t e = cudaFuncSetAttribute(k_point_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_point_scatter<<<he_count, 256, smem, st>>>(P, he_begin, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info,
+                                               out);
   return cudaGetLastError();
 }
 

@@ -7,7 +7,7 @@
 
 namespace atm {
 
-constexpr int kMaxDirs = 2048;  // sphere quadrature directions the point-scatter kernel keeps in shared memory
+constexpr int kMaxDirs = 1536;  // sphere quadrature directions the point-scatter kernel keeps in shared memory
 
 // one output of the first-order kernel: ray-scatter of point-scatter-component (strength = 0) or
 // strength-component (strength = 1) of scatter[component]
@@ -50,9 +50,14 @@ cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, cons
                                unsigned long long *counter, cudaStream_t st);
 cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
                                          cudaStream_t st);
-cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, SSource src, const float4 *de,
-                                 const double *dirs, const double *weights, int ndirs, const DirInfo *info,
-                                 float4 *out, cudaStream_t st);
+cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, float4 *tiles,
+                                   cudaStream_t st);
+// tiles_a / tiles_b: blended [height][direction][light-elevation][heading] tiles of the S source
+cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, const float4 *tiles_a,
+                                 const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
+                                 const double *weights, int ndirs, const DirInfo *info, float4 *out,
+                                 cudaStream_t st);
+size_t ray_scatter_smem(const Params &P);
 cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,
                                             cudaStream_t st);
 cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *dirs, const double *weights,
