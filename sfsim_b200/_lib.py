@@ -10,7 +10,7 @@ import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_NAME = "libsfsim_atmosphere.so"
-LIB_PATH = os.path.join(_ROOT, LIB_NAME)
+LIB_PATH = os.environ.get("SFSIM_ATMOSPHERE_LIB", os.path.join(_ROOT, LIB_NAME))
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)

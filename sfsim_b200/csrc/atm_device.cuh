@@ -5,8 +5,17 @@
 
 #include "atm_math.cuh"
 
+#ifndef ATMLUT_SAMPLER_UNROLL
+#define ATMLUT_SAMPLER_UNROLL 4
+#endif
+
+#ifndef ATMLUT_SAMPLER_UNROLL
+#define ATMLUT_SAMPLER_UNROLL 4
+#endif
+
 namespace atm {
 
+constexpr int kSamplerUnroll = ATMLUT_SAMPLER_UNROLL;   // 4-sample groups per loop trip of the hot sampler
 constexpr int kMaxSteps = 256;       // ray_steps limit of the table kernels (shared-memory arrays)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -104,33 +113,69 @@ __device__ __forceinline__ void density_sums_strided(const Params &P, const Quad
   }
 }
 
-// Sequential variant (one thread per segment): forward differences in double (two DADD per
-// sample), four interleaved accumulators per component.
+// exp(-h/scale_c) of TWO samples at once with Blackwell's packed FP32 instructions (FFMA2 / FMUL2:
+// one issue slot for two lanes of work).  The loop is co-limited by issue slots and the MUFU pipe; packing
+// the polynomial takes it off the issue limit.
+__device__ __forceinline__ void densities_from_u2(const Fast &f, float2 u, float2 &e0, float2 &e1) {
+  float2 q = __ffma2_rn(u, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
+  q = __ffma2_rn(q, u, make_float2(0.0625f, 0.0625f));
+  q = __ffma2_rn(q, u, make_float2(-0.125f, -0.125f));
+  q = __ffma2_rn(q, u, make_float2(0.5f, 0.5f));
+  const float2 hq = __fmul2_rn(u, q);  // h' / R'
+  const float2 a0 = __ffma2_rn(hq, make_float2(f.k[0], f.k[0]), make_float2(f.b[0], f.b[0]));
+  const float2 a1 = __ffma2_rn(hq, make_float2(f.k[1], f.k[1]), make_float2(f.b[1], f.b[1]));
+  e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+  e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+}
+
+// Sequential variant (one thread per segment): u(m) advances by forward differences in double, two
+// samples per step (2 DADD per pair); the odd sample's u is the even one's float image plus the float
+// first difference.  Packed accumulators, two independent pairs in flight.
 __device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
   if (P.fast.poly) {
-    double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // m = 1/2
-    double d1 = q.B + 2.0 * q.C;                     // u(m+1) - u(m) at m = 1/2
-    const double d2 = 2.0 * q.C;
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, e0 = 0.f, e1 = 0.f;
+    double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // u at m = 1/2
+    const double d1 = q.B + 2.0 * q.C;               // u(m+1) - u(m) at m = 1/2
+    const double d2 = 2.0 * q.C;                     // second difference
+    double step2 = 2.0 * d1 + d2;                    // u(m+2) - u(m)
+    const double step2_inc = 4.0 * d2;
+    float d1f = (float)d1;                           // first difference at the even sample, in float
+    const float d1f_inc = (float)(2.0 * d2);
+    float2 acc0a = make_float2(0.f, 0.f), acc1a = make_float2(0.f, 0.f);
+    float2 acc0b = make_float2(0.f, 0.f), acc1b = make_float2(0.f, 0.f);
     int j = 0;
+#pragma unroll kSamplerUnroll
     for (; j + 4 <= steps; j += 4) {
-      float x0, x1;
-      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-      a0 += x0; a1 += x1; u += d1; d1 += d2;
-      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-      b0 += x0; b1 += x1; u += d1; d1 += d2;
-      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-      c0 += x0; c1 += x1; u += d1; d1 += d2;
-      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-      e0 += x0; e1 += x1; u += d1; d1 += d2;
+      float2 e0, e1;
+      float ue = trunc_d2f(u);
+      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
+      acc0a = __fadd2_rn(acc0a, e0);
+      acc1a = __fadd2_rn(acc1a, e1);
+      u += step2;
+      step2 += step2_inc;
+      d1f += d1f_inc;
+      ue = trunc_d2f(u);
+      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
+      acc0b = __fadd2_rn(acc0b, e0);
+      acc1b = __fadd2_rn(acc1b, e1);
+      u += step2;
+      step2 += step2_inc;
+      d1f += d1f_inc;
     }
-    for (; j < steps; j++) {
-      float x0, x1;
-      densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-      a0 += x0; a1 += x1; u += d1; d1 += d2;
+    float t0 = 0.f, t1 = 0.f;
+    if (j < steps) {
+      // tail of up to 3 samples, one at a time: u(m+1) = u(m) + d1(m)
+      double d1m = d1 + (double)j * d2;
+      for (; j < steps; j++) {
+        float x0, x1;
+        densities_from_u(P.fast, trunc_d2f(u), x0, x1);
+        t0 += x0;
+        t1 += x1;
+        u += d1m;
+        d1m += d2;
+      }
     }
-    s0 = (a0 + b0) + (c0 + e0);
-    s1 = (a1 + b1) + (c1 + e1);
+    s0 = ((acc0a.x + acc0b.x) + (acc0a.y + acc0b.y)) + t0;
+    s1 = ((acc1a.x + acc1b.x) + (acc1a.y + acc1b.y)) + t1;
   } else {
     s0 = 0.f;
     s1 = 0.f;

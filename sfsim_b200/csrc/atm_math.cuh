@@ -208,6 +208,13 @@ HD V3 index_to_height(const Planet &p, int size, double index) {
 HD double sin_sun_elevation_to_index(int size, double sin_elevation) {
   return (double)(size - 1) * fmax(0.0, (1 - exp(0 - 3 * sin_elevation - 0.6)) / (1 - exp(-3.6)));
 }
+// Same map for the lookups inside the integration kernels: the division by the constant 1 - exp(-3.6) is a
+// multiplication by its reciprocal (the result is continuous in the coordinate and the clamp to exactly 0
+// happens before the scaling, so the one-ulp difference cannot change a table value beyond rounding).
+HD double sin_sun_elevation_to_index_fast(int size, double sin_elevation) {
+  const double inv = 1.0 / (1 - 0.02732372244729256);   // 1 / (1 - exp(-3.6))
+  return (double)(size - 1) * fmax(0.0, (1 - exp(0 - 3 * sin_elevation - 0.6)) * inv);
+}
 HD double sun_elevation_to_index(int size, V3 point, V3 light) {
   return sin_sun_elevation_to_index(size, dot(point, light) / mag(point));
 }

@@ -12,6 +12,9 @@
 // transmittance samples of one view ray lie on that ray, which is a function of the (height,
 // elevation) texel pair only, so one CTA owns one (height, elevation) pair, integrates the view
 // ray once into shared memory and then serves all (light-elevation, heading) texels from it.
+#include <algorithm>
+#include <cstdlib>
+
 #include "atm_device.cuh"
 #include "atm_tables.h"
 
@@ -135,111 +138,144 @@ __global__ void k_surface_radiance_base(Params P, float4 *out) {
 
 // ------------------------------------------------------------------ K3: first-order ray scatter
 
-// One CTA per (height, elevation) pair, one thread per (light-elevation, heading) texel (optionally
-// split into `kparts` ranges of the outer sample index when the pair has few texels).
-// acc_c[ch] = sum_k exp(-h(p_k)/scale_c) T(x->p_k)[ch] T(p_k->sun)[ch] [sun visible from p_k]
-__global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int kparts, FirstOrderOut oa,
-                                                     FirstOrderOut ob, unsigned long long *counter) {
+// acc_c[ch] = sum over outer samples k in [k0, k1) of
+//   exp(-h(p_k)/scale_c) T(x->p_k)[ch] T(p_k->sun)[ch] [sun visible from p_k]
+// for the texel with light direction l (atmosphere.clj:192-200 with the first-order sources :140-182).
+__device__ __forceinline__ void first_order_texel(const Params &P, const ViewSmem &vs, V3 l, int k0, int k1,
+                                                  float acc0[3], float acc1[3], unsigned &esamples) {
+  const int steps = P.shapes.ray_steps;
+  const double rt2 = sqr(P.planet.radius + P.planet.height);
+  const double r2 = sqr(P.planet.radius);
+  const double inv_steps = 1.0 / (double)steps;
+  const double ll = dot(l, l);
+  const double llen = sqrt(ll);
+  for (int k = k0; k < k1; k++) {
+    const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
+    const double pl = l.x * pkx + l.y * pky;
+    // filtered-sun-light (atmosphere.clj:154-160): is-above-horizon? (p_k, l)
+    if (!(pl >= 0 || pl * pl <= rk2 - r2)) continue;
+    // atmosphere-intersection of (p_k, l) (atmosphere.clj:70-77, sphere.clj:46-59)
+    const double disc = pl * pl - ll * (rk2 - rt2);
+    const double middle = -(pl / ll);
+    double t;
+    if (disc > 0) {
+      double length2 = sqrt(disc) / ll;
+      t = (middle < length2) ? fmax(0.0, middle + length2) : (middle - length2) + 2 * length2;
+    } else {
+      t = fmax(0.0, middle);
+    }
+    // transmittance p_k -> end point: samples p_k + (l t)(j + 1/2)/steps
+    Quad q = make_quad(P.fast, rk2, pl * t, ll * t * t, steps);
+    float s0, s1;
+    density_sums_seq(P, q, steps, s0, s1);
+    esamples += steps;
+    const float seg = (float)(t * llen * inv_steps);
+    float tr[3];
+    transmittance_rgb(P.fast, fmaf(s0, seg, vs.cv0[k]), fmaf(s1, seg, vs.cv1[k]), tr);
+    const float d0 = vs.dens0[k], d1 = vs.dens1[k];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      acc0[ch] = fmaf(d0, tr[ch], acc0[ch]);
+      acc1[ch] = fmaf(d1, tr[ch], acc1[ch]);
+    }
+  }
+}
+
+// ray.clj:19-30: every term carries a = stepsize * |direction|; the source's constant factors
+// (scatter-base, phase, intensity) are applied once per texel
+__device__ __forceinline__ void first_order_store(const Params &P, const ViewRay &ray, V3 v, V3 l, size_t idx,
+                                                  const float acc0[3], const float acc1[3], FirstOrderOut oa,
+                                                  FirstOrderOut ob) {
+  const double a = ray.dlen / (double)P.shapes.ray_steps;
+  const double mu = dot(v, l);
+  FirstOrderOut outs[2] = {oa, ob};
+#pragma unroll
+  for (int o = 0; o < 2; o++) {
+    if (!outs[o].table) continue;
+    const int c = outs[o].component;
+    const float *acc = c ? acc1 : acc0;
+    const double ph = outs[o].strength ? 1.0 : phase(P.medium.g[c], mu);
+    float4 val;
+    val.x = (float)(P.medium.base[c][0] * ph * P.intensity[0] * a * (double)acc[0]);
+    val.y = (float)(P.medium.base[c][1] * ph * P.intensity[1] * a * (double)acc[1]);
+    val.z = (float)(P.medium.base[c][2] * ph * P.intensity[2] * a * (double)acc[2]);
+    val.w = 0.0f;
+    outs[o].table[idx] = val;
+  }
+}
+
+// First-order ray scatter of both sources in one pass.  A (height, elevation) pair is served by `nchunks`
+// CTAs; each integrates the view ray once into shared memory (setup_view_ray) and then every warp takes
+// `passes` groups of 32 (light-elevation, heading) texels.  Texels are light-elevation major and low sun
+// rows skip most samples (sun below the local horizon), so group cost grows with the group index: groups
+// are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
+// while each group stays a coherent row block (no extra divergence).
+// kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
+__global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int kparts, int passes, int nchunks,
+                                                     FirstOrderOut oa, FirstOrderOut ob,
+                                                     unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
   float *partial = reinterpret_cast<float *>(smem_raw + sizeof(ViewSmem));  // [6][blockDim] when kparts > 1
   const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
-  const int he = he_begin + blockIdx.x;
+  const int ntex = S * A;
+  const int he = he_begin + blockIdx.x / nchunks;
+  const int chunk = blockIdx.x % nchunks;
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
   setup_view_ray(P, h, e, vs, esamples);
   const ViewRay ray = vs.ray;
-  const int ntex = S * A;
-  const int items = ntex * kparts;
-  const double rt2 = sqr(P.planet.radius + P.planet.height);
-  const double r2 = sqr(P.planet.radius);
-  const double inv_steps = 1.0 / (double)steps;
+  const V3 v = v3(ray.vx, ray.vy, 0.0);
 
-  for (int base = 0; base < items; base += blockDim.x) {
-    const int item = base + threadIdx.x;
+  if (kparts == 1) {
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_warps = nchunks * nwarps;            // warps serving this pair
+    const int wg = chunk * nwarps + warp;
+    const int ngroups = (ntex + 31) >> 5;
+    for (int pass = 0; pass < passes; pass++) {
+      const int group = pass * total_warps + ((pass & 1) ? total_warps - 1 - wg : wg);
+      const int texel = group * 32 + lane;
+      if (group >= ngroups || texel >= ntex) continue;
+      const int si = texel / A, ai = texel % A;
+      const double ss = index_to_sin_sun_elevation(S, (double)si);
+      const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+      float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
+      first_order_texel(P, vs, l, 0, steps, acc0, acc1, esamples);
+      first_order_store(P, ray, v, l, (size_t)he * ntex + texel, acc0, acc1, oa, ob);
+    }
+  } else {
+    const int items = ntex * kparts;
+    const int item = threadIdx.x;
     const bool active = item < items;
     const int texel = active ? item % ntex : 0;
     const int part = active ? item / ntex : 0;
     float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
-    V3 v = v3(ray.vx, ray.vy, 0.0);
     V3 l = v3(0, 0, 0);
     if (active) {
       const int si = texel / A, ai = texel % A;
-      double ss = index_to_sin_sun_elevation(S, (double)si);
+      const double ss = index_to_sin_sun_elevation(S, (double)si);
       l = index_to_sun_direction(A, v, ss, (double)ai);
-      const double ll = dot(l, l);
-      const double llen = sqrt(ll);
       const int k0 = (int)(((long long)steps * part) / kparts), k1 = (int)(((long long)steps * (part + 1)) / kparts);
-      for (int k = k0; k < k1; k++) {
-        const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
-        const double pl = l.x * pkx + l.y * pky;
-        // filtered-sun-light (atmosphere.clj:154-160): is-above-horizon? (p_k, l)
-        if (!(pl >= 0 || pl * pl <= rk2 - r2)) continue;
-        // atmosphere-intersection of (p_k, l) (atmosphere.clj:70-77, sphere.clj:46-59)
-        const double disc = pl * pl - ll * (rk2 - rt2);
-        const double middle = -(pl / ll);
-        double t;
-        if (disc > 0) {
-          double length2 = sqrt(disc) / ll;
-          t = (middle < length2) ? fmax(0.0, middle + length2) : (middle - length2) + 2 * length2;
-        } else {
-          t = fmax(0.0, middle);
-        }
-        // transmittance p_k -> end point: samples p_k + (l t)(j + 1/2)/steps
-        Quad q = make_quad(P.fast, rk2, pl * t, ll * t * t, steps);
-        float s0, s1;
-        density_sums_seq(P, q, steps, s0, s1);
-        esamples += steps;
-        const float seg = (float)(t * llen * inv_steps);
-        float tr[3];
-        transmittance_rgb(P.fast, fmaf(s0, seg, vs.cv0[k]), fmaf(s1, seg, vs.cv1[k]), tr);
-        const float d0 = vs.dens0[k], d1 = vs.dens1[k];
+      first_order_texel(P, vs, l, k0, k1, acc0, acc1, esamples);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      partial[ch * blockDim.x + threadIdx.x] = acc0[ch];
+      partial[(3 + ch) * blockDim.x + threadIdx.x] = acc1[ch];
+    }
+    __syncthreads();
+    if (active && part == 0) {
+      for (int p = 1; p < kparts; p++) {
+        const int other = p * ntex + texel;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-          acc0[ch] = fmaf(d0, tr[ch], acc0[ch]);
-          acc1[ch] = fmaf(d1, tr[ch], acc1[ch]);
+          acc0[ch] += partial[ch * blockDim.x + other];
+          acc1[ch] += partial[(3 + ch) * blockDim.x + other];
         }
       }
-    }
-    if (kparts > 1) {
-      __syncthreads();
-#pragma unroll
-      for (int ch = 0; ch < 3; ch++) {
-        partial[ch * blockDim.x + threadIdx.x] = acc0[ch];
-        partial[(3 + ch) * blockDim.x + threadIdx.x] = acc1[ch];
-      }
-      __syncthreads();
-      if (active && part == 0) {
-        for (int p = 1; p < kparts; p++) {
-          int other = p * ntex + texel - base;
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            acc0[ch] += partial[ch * blockDim.x + other];
-            acc1[ch] += partial[(3 + ch) * blockDim.x + other];
-          }
-        }
-      }
-    }
-    if (active && part == 0) {
-      // ray.clj:19-30: every term carries a = stepsize * |direction|
-      const double a = inv_steps * ray.dlen;
-      const double mu = dot(v, l);
-      const size_t idx = (size_t)he * ntex + texel;
-      FirstOrderOut outs[2] = {oa, ob};
-#pragma unroll
-      for (int o = 0; o < 2; o++) {
-        if (!outs[o].table) continue;
-        const int c = outs[o].component;
-        const float *acc = c ? acc1 : acc0;
-        const double ph = outs[o].strength ? 1.0 : phase(P.medium.g[c], mu);
-        float4 val;
-        val.x = (float)(P.medium.base[c][0] * ph * P.intensity[0] * a * (double)acc[0]);
-        val.y = (float)(P.medium.base[c][1] * ph * P.intensity[1] * a * (double)acc[1]);
-        val.z = (float)(P.medium.base[c][2] * ph * P.intensity[2] * a * (double)acc[2]);
-        val.w = 0.0f;
-        outs[o].table[idx] = val;
-      }
+      first_order_store(P, ray, v, l, (size_t)he * ntex + texel, acc0, acc1, oa, ob);
     }
   }
   count_esamples(counter, esamples);
@@ -248,10 +284,11 @@ __global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int
 // ------------------------------------------------------------------ K6: ray scatter from the dJ table
 
 struct alignas(16) LookupSmem {
-  int hu[kMaxSteps], hv[kMaxSteps], eu[kMaxSteps], ev[kMaxSteps];
+  int row[kMaxSteps][4];       // element offsets of the (height, elevation) corner tiles (hu,eu) (hu,ev) (hv,eu) (hv,ev)
   float hs[kMaxSteps], es[kMaxSteps];
   float tr[kMaxSteps][3];      // T(x -> p_k)
   double rk[kMaxSteps];        // |p_k|
+  double nx[kMaxSteps], ny[kMaxSteps];   // p_k / |p_k|
 };
 
 // dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with
@@ -281,11 +318,12 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, co
     V3 p = v3(vs.pkx[k], vs.pky[k], 0.0);
     Axis ah = axis_from(height_to_index(P.planet, H, p), H);
     Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
-    ls.hu[k] = ah.u;
-    ls.hv[k] = ah.v;
+    const int tile_elems = S * A;
+    ls.row[k][0] = (ah.u * E + ae.u) * tile_elems;
+    ls.row[k][1] = (ah.u * E + ae.v) * tile_elems;
+    ls.row[k][2] = (ah.v * E + ae.u) * tile_elems;
+    ls.row[k][3] = (ah.v * E + ae.v) * tile_elems;
     ls.hs[k] = ah.s;
-    ls.eu[k] = ae.u;
-    ls.ev[k] = ae.v;
     ls.es[k] = ae.s;
     float tr[3];
     transmittance_rgb(P.fast, vs.cv0[k], vs.cv1[k], tr);
@@ -293,6 +331,8 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, co
     ls.tr[k][1] = tr[1];
     ls.tr[k][2] = tr[2];
     ls.rk[k] = sqrt(vs.rk2[k]);
+    ls.nx[k] = vs.pkx[k] / ls.rk[k];
+    ls.ny[k] = vs.pky[k] / ls.rk[k];
   }
   __syncthreads();
   const int ntex = S * A;
@@ -308,21 +348,22 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, co
     for (int k = 0; k < steps; k++) {
       float4 *tile = tiles + (size_t)(k & 1) * ntex;
       {
-        const size_t r00 = ((size_t)ls.hu[k] * E + ls.eu[k]) * ntex, r01 = ((size_t)ls.hu[k] * E + ls.ev[k]) * ntex;
-        const size_t r10 = ((size_t)ls.hv[k] * E + ls.eu[k]) * ntex, r11 = ((size_t)ls.hv[k] * E + ls.ev[k]) * ntex;
+        const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k]);
+        const float4 *t00 = dj + rows.x, *t01 = dj + rows.y, *t10 = dj + rows.z, *t11 = dj + rows.w;
         const float es = ls.es[k], hs = ls.hs[k];
         for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
-          tile[idx] = mix4(mix4(ldg4(dj + r00 + idx), ldg4(dj + r01 + idx), es),
-                           mix4(ldg4(dj + r10 + idx), ldg4(dj + r11 + idx), es), hs);
+          tile[idx] = mix4(mix4(ldg4(t00 + idx), ldg4(t01 + idx), es), mix4(ldg4(t10 + idx), ldg4(t11 + idx), es), hs);
       }
       __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
       if (active) {
-        const double pl = l.x * vs.pkx[k] + l.y * vs.pky[k];
-        // the sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
-        // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.  The
-        // true division keeps it bit-identical to the reference's (dot p l) / (mag p), so that rows the
-        // reference clamps to exactly 0 are clamped here as well.
-        const Axis as = axis_from(sin_sun_elevation_to_index(S, pl / ls.rk[k]), S);
+        // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
+        // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.
+        // sin = l . (p_k / |p_k|) with the unit vector precomputed per sample; only next to the lower clamp
+        // (sin = -0.2, coordinate 0) it is recomputed as the reference writes it, (dot p l) / (mag p), so
+        // that rows the reference clamps to exactly 0 are clamped here as well.
+        double sin_elev = l.x * ls.nx[k] + l.y * ls.ny[k];
+        if (sin_elev < -0.2 + 1e-9) sin_elev = (l.x * vs.pkx[k] + l.y * vs.pky[k]) / ls.rk[k];
+        const Axis as = axis_from(sin_sun_elevation_to_index_fast(S, sin_elev), S);
         const float4 j = lookup2_smem(tile, A, as, aa);
         acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
         acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
@@ -491,7 +532,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, c
         eh.v = r.ehv;
         eh.s = r.ehs;
         double sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
-        Axis es = axis_from(sin_sun_elevation_to_index(P.shapes.se[1], sin_elev), P.shapes.se[1]);
+        Axis es = axis_from(sin_sun_elevation_to_index_fast(P.shapes.se[1], sin_elev), P.shapes.se[1]);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
         s.x = fmaf(r.tb[0], ev.x, s.x);
         s.y = fmaf(r.tb[1], ev.y, s.y);
@@ -677,25 +718,30 @@ cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStrea
   return cudaGetLastError();
 }
 
-static int first_order_kparts(const Params &P, int threads) {
-  int ntex = P.shapes.s4[2] * P.shapes.s4[3];
-  if (ntex >= threads) return 1;
-  int kp = threads / ntex;
-  return kp < P.shapes.ray_steps ? kp : P.shapes.ray_steps;
+static int env_int(const char *name, int fallback) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : fallback;
 }
 
 cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, FirstOrderOut oa, FirstOrderOut ob,
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
-  const int threads = 256;
-  int kparts = first_order_kparts(P, threads);
-  size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_first_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ViewSmem) + 6 * 256 * 4));
-    attr = true;
+  // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
+  static const int warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 4)));
+  static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 2));
+  const int threads = warps * 32;
+  const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
+  int kparts = 1, passes = 1, nchunks = 1;
+  if (ntex < threads) {
+    kparts = std::min(P.shapes.ray_steps, threads / ntex);
+  } else {
+    const int ngroups = (ntex + 31) / 32;
+    passes = std::min(want_passes, (ngroups + warps - 1) / warps);
+    const int total_warps = (ngroups + passes - 1) / passes;
+    nchunks = (total_warps + warps - 1) / warps;
   }
-  k_first_order<<<he_count, threads, smem, st>>>(P, he_begin, kparts, oa, ob, counter);
+  size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
+  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, he_begin, kparts, passes, nchunks, oa, ob, counter);
   return cudaGetLastError();
 }
 
