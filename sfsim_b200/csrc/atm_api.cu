@@ -89,6 +89,8 @@ int make_params(const atmlut_planet *planet, const atmlut_scatter *scatter, int 
     if (sizes[i] < 2) return fail("every table axis needs at least 2 entries");
   if (cfg->ray_steps < 1 || cfg->ray_steps > kMaxSteps) return fail("ray_steps must be in [1, 256]");
   if (cfg->sphere_steps < 2) return fail("sphere_steps must be at least 2");
+  if ((long long)cfg->height_size * cfg->elevation_size * cfg->light_elevation_size * cfg->heading_size > (1LL << 28))
+    return fail("the 4-D table must not exceed 2^28 texels");
   if ((long long)cfg->light_elevation_size * cfg->heading_size > 6144)
     return fail("light_elevation_size * heading_size must not exceed 6144 (shared-memory tile of the ray-scatter kernel)");
   for (int i = 0; i < 4; i++) P.shapes.s4[i] = sizes[i];

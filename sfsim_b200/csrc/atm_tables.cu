@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(256) k_blend_dir_tiles(Params P, const float4 
 struct alignas(16) PointDir {
   double ox, oy, oz;      // omega_d
   double px, py, pz, pm;  // ray extremity and its norm (surface directions)
+  double ux, uy, uz;      // ray extremity / norm
   float sc[3];            // weight_d * sum_c scattering_c(h(x)) phase_c(v . omega_d)
   float tb[3];            // T(x -> point) * brightness / pi
   int surface;
@@ -502,11 +503,15 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, c
     r.py = di.ny;
     r.pz = di.nz;
     r.pm = di.nmag;
+    r.ux = di.nx / di.nmag;
+    r.uy = di.ny / di.nmag;
+    r.uz = di.nz / di.nmag;
     pd[d] = r;
   }
   __syncthreads();
   const int ntex = S * A;
   const size_t tile_base = (size_t)h * ndirs * ntex;
+  const float phase_c0 = (float)((3.0 * (1.0 - phase_g * phase_g)) / (8.0 * kPi * (2.0 + phase_g * phase_g)));
   for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
     const int si = texel / A, ai = texel % A;
     double ss = index_to_sin_sun_elevation(S, (double)si);
@@ -520,7 +525,9 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, c
       float4 s = lookup2(tiles_a + tile_base + (size_t)d * ntex, A, as, aa);
       if (tiles_b) {
         float4 m = lookup2(tiles_b + tile_base + (size_t)d * ntex, A, as, aa);
-        float ph = (float)phase(phase_g, mu);
+        // phase (atmosphere.clj:56-61) with the cancellation-prone base in double and the rest in float
+        const float base = (float)((1.0 + phase_g * phase_g) - 2.0 * phase_g * mu);
+        const float ph = phase_c0 * (float)(1.0 + mu * mu) / (base * sqrtf(base));
         s.x = fmaf(m.x, ph, s.x);
         s.y = fmaf(m.y, ph, s.y);
         s.z = fmaf(m.z, ph, s.z);
@@ -531,7 +538,10 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, c
         eh.u = r.ehu;
         eh.v = r.ehv;
         eh.s = r.ehs;
-        double sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
+        // sine of the sun elevation at the ground point: unit vector precomputed per direction; next to the
+        // lower clamp it is recomputed as the reference writes it, (dot point l) / (mag point)
+        double sin_elev = r.ux * l.x + r.uy * l.y + r.uz * l.z;
+        if (sin_elev < -0.2 + 1e-9) sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
         Axis es = axis_from(sin_sun_elevation_to_index_fast(P.shapes.se[1], sin_elev), P.shapes.se[1]);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
         s.x = fmaf(r.tb[0], ev.x, s.x);
@@ -590,7 +600,9 @@ __global__ void __launch_bounds__(256) k_surface_radiance(Params P, SSource src,
     float4 s = lookup4(src.tab_a, P.shapes.s4, ah, ae, as, aa);
     if (src.tab_b) {
       float4 mm = lookup4(src.tab_b, P.shapes.s4, ah, ae, as, aa);
-      float ph = (float)phase(src.phase_g, mu);
+      const float base = (float)((1.0 + src.phase_g * src.phase_g) - 2.0 * src.phase_g * mu);
+      const float ph = (float)((3.0 * (1.0 - src.phase_g * src.phase_g)) / (8.0 * kPi * (2.0 + src.phase_g * src.phase_g))) *
+                       (float)(1.0 + mu * mu) / (base * sqrtf(base));
       s.x = fmaf(mm.x, ph, s.x);
       s.y = fmaf(mm.y, ph, s.y);
       s.z = fmaf(mm.z, ph, s.z);
