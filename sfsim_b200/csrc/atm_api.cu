@@ -147,7 +147,9 @@ struct Builder {
   void *allgather_user = nullptr;
   // device tables (float4)
   float4 *T = nullptr, *dE = nullptr, *dE_new = nullptr, *Eacc = nullptr, *Eacc_new = nullptr;
-  float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
+  float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dS2 = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
+  cudaStream_t side = nullptr;             // second stream of the build DAG
+  std::vector<cudaEvent_t> events;         // ordering events between the two streams
   float *file_T = nullptr, *file_E = nullptr, *file_S = nullptr, *file_M = nullptr;
   double *sphere_dirs = nullptr, *sphere_w = nullptr, *half_dirs = nullptr, *half_w = nullptr;
   int n_sphere = 0, n_half = 0;
@@ -162,7 +164,7 @@ struct Builder {
   long long launches = 0;   // kernels launched by the last run
 
   ~Builder() {
-    void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dJ, S, S_new, file_T, file_E, file_S, file_M,
+    void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dS2, dJ, S, S_new, file_T, file_E, file_S, file_M,
                     sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
                     tiles_a, tiles_b};
     for (void *p : ptrs)
@@ -171,6 +173,8 @@ struct Builder {
       cudaEventDestroy(s.begin);
       cudaEventDestroy(s.end);
     }
+    for (auto e : events) cudaEventDestroy(e);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -204,7 +208,8 @@ static int builder_alloc(Builder &b) {
   b.n4_pad = (long long)b.he_per_rank * b.world * b.ntex;
   b.nt = (long long)P.shapes.st[0] * P.shapes.st[1];
   b.ne = (long long)P.shapes.se[0] * P.shapes.se[1];
-  float4 **four[] = {&b.R1, &b.M1, &b.dS, &b.dJ, &b.S, &b.S_new};
+  CUDA_TRY(cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking));
+  float4 **four[] = {&b.R1, &b.M1, &b.dS, &b.dS2, &b.dJ, &b.S, &b.S_new};
   for (auto p : four) {
     if (dev_alloc(*p, (size_t)b.n4_pad)) return 1;
     CUDA_TRY(cudaMemsetAsync(*p, 0, (size_t)b.n4_pad * sizeof(float4), g_stream));
@@ -269,25 +274,62 @@ static int gather(Builder &b, float4 *table) {
     b.launches++;     \
   } while (0)
 
-// generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below)
+// event pool: events are created on first use and reused by later runs
+static int event_at(Builder &b, size_t index, cudaEvent_t &ev) {
+  while (b.events.size() <= index) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    b.events.push_back(e);
+  }
+  ev = b.events[index];
+  return 0;
+}
+
+// record an event on `from` and make `to` wait for it
+static int order_after(Builder &b, size_t &cursor, cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t ev;
+  if (event_at(b, cursor++, ev)) return 1;
+  CUDA_TRY(cudaEventRecord(ev, from));
+  CUDA_TRY(cudaStreamWaitEvent(to, ev, 0));
+  return 0;
+}
+
+// generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below).
+//
+// Two streams.  The MAIN stream carries the chain that bounds the build:
+//     first-order ray scatter -> [ blend tiles -> point scatter (dJ) -> ray scatter (dS) ] x iterations
+// with one all-gather per sharded table.  Everything that merely hangs off that chain runs on the SIDE
+// stream, concurrently with the heavy kernels: the 2-D tables and per-direction constants (needed by the
+// first point-scatter only), surface radiance dE_n = f(dS_{n-1}) (needed by the NEXT point scatter), the
+// re-tabulated sums E += dE and S += dS (needed only at the very end), and the final file-layout tables.
+// dS and dE are double buffered so the side stream can still read order n-1 while order n is written.
 static int builder_run(Builder &b) {
   const Params &P = b.P;
-  cudaStream_t st = g_stream;
+  cudaStream_t st = g_stream, side = b.side;
   b.stage_cursor = 0;
   b.launches = 0;
+  size_t ev = 0;
+  const int E = P.shapes.s4[1];
+  const int h_first = b.he_count > 0 ? b.he_begin / E : 0;
+  const int h_count = b.he_count > 0 ? (b.he_begin + b.he_count - 1) / E - h_first + 1 : 0;
+  float4 *dsbuf[2] = {b.dS, b.dS2};
+  float4 *debuf[2] = {b.dE, b.dE_new};
+  const int N = b.iterations;
+
   CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
-  const long long slab_begin = (long long)b.he_begin * b.ntex, slab_count = (long long)b.he_count * b.ntex;
-  (void)slab_begin;
-  (void)slab_count;
+  TRY(order_after(b, ev, st, side));   // the side stream starts after whatever the main stream did before
 
-  TRY(stage_begin(b, "transmittance+surface_radiance_base"));
-  LAUNCH(launch_transmittance_table(P, b.T, st));                                     // :74
-  LAUNCH(launch_surface_radiance_base(P, b.dE, st));                                  // :75
-  CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), st));            // :76 E = 0
-  LAUNCH(launch_point_scatter_prepare(P, b.sphere_dirs, b.n_sphere, b.dir_info, st));
-  if (b.n_half > 0) LAUNCH(launch_surface_radiance_prepare(P, b.half_dirs, b.n_half, b.half_info, st));
-  TRY(stage_end(b));
+  // ---- side: 2-D tables and per-direction constants
+  LAUNCH(launch_transmittance_table(P, b.T, side));                                   // :74
+  LAUNCH(launch_surface_radiance_base(P, debuf[0], side));                            // :75  dE_0
+  LAUNCH(launch_point_scatter_prepare(P, b.sphere_dirs, b.n_sphere, b.dir_info, side));
+  if (b.n_half > 0) LAUNCH(launch_surface_radiance_prepare(P, b.half_dirs, b.n_half, b.half_info, side));
+  cudaEvent_t e_prepared;
+  TRY(event_at(b, ev++, e_prepared));
+  CUDA_TRY(cudaEventRecord(e_prepared, side));
+  LAUNCH(launch_resample_2d(P, 2, b.T, nullptr, nullptr, b.file_T, side));            // :98,102
 
+  // ---- main: first order
   TRY(stage_begin(b, "first_order"));
   FirstOrderOut rayleigh = {b.R1, 1, 0};                                              // :68,71,77
   FirstOrderOut mie_strength = {b.M1, 0, 1};                                          // :69,72,78
@@ -298,52 +340,84 @@ static int builder_run(Builder &b) {
   TRY(gather(b, b.M1));
   TRY(stage_end(b));
 
-  SSource ds = {b.R1, b.M1, P.medium.g[0]};                                           // :79-84
-  const float4 *s_cur = b.R1;                                                         // :85
-  for (int it = 0; it < b.iterations; it++) {                                         // :86
+  SSource ds = {b.R1, b.M1, P.medium.g[0]};                                           // :79-84  dS_0
+  const float4 *s_cur = b.R1;                                                         // :85     S_0
+  const float4 *e_cur = nullptr;                                                      // :76     E_0 = 0
+  std::vector<cudaEvent_t> side_done(N + 1, nullptr);   // side finished reading dS_n
+  std::vector<cudaEvent_t> de_ready(N + 1, nullptr);    // dE_n written
+  de_ready[0] = e_prepared;
+
+  for (int it = 0; it < N; it++) {                                                    // :86
     char name[64];
+    // ---- side, order it: dE_{it+1} = surface-radiance(dS_it), E += dE, S += dS_it (all read dS_it)
+    TRY(order_after(b, ev, st, side));                                                // dS_it is complete
+    if (it == 0) CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
+    float4 *de_next = debuf[(it + 1) & 1];
+    if (b.n_half > 0)
+      LAUNCH(launch_surface_radiance(P, ds, b.half_dirs, b.half_w, b.n_half, b.half_info, de_next, side));  // :89,92
+    else
+      CUDA_TRY(cudaMemsetAsync(de_next, 0, (size_t)b.ne * sizeof(float4), side));
+    TRY(event_at(b, ev++, de_ready[it + 1]));
+    CUDA_TRY(cudaEventRecord(de_ready[it + 1], side));
+    LAUNCH(launch_resample_2d(P, 1, e_cur, de_next, b.Eacc_new, nullptr, side));      // :94-95
+    std::swap(b.Eacc, b.Eacc_new);
+    e_cur = b.Eacc;
+    if (it == 0) {
+      LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, side)); // :101,105
+    } else {
+      LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, ds.tab_a, b.S_new, nullptr, side));  // :96-97
+      std::swap(b.S, b.S_new);
+      s_cur = b.S;
+    }
+    TRY(event_at(b, ev++, side_done[it]));
+    CUDA_TRY(cudaEventRecord(side_done[it], side));
+
+    // ---- main: dJ_{it+1} = point-scatter(dS_it, dE_it)
     snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
     TRY(stage_begin(b, name));
-    LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, b.tiles_a, st));
-    if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, b.tiles_b, st));
-    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g, b.dE,
-                                b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.dJ, st));  // :88,90
+    CUDA_TRY(cudaStreamWaitEvent(st, de_ready[it], 0));
+    if (h_count > 0) {
+      LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_a, st));
+      if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_b, st));
+    }
+    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
+                                debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.dJ, st));  // :88,90
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_point_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
     TRY(gather(b, b.dJ));
     TRY(stage_end(b));
-    snprintf(name, sizeof name, "iter%d_surface_radiance", it + 1);
-    TRY(stage_begin(b, name));
-    if (b.n_half > 0)
-      LAUNCH(launch_surface_radiance(P, ds, b.half_dirs, b.half_w, b.n_half, b.half_info, b.dE_new, st));  // :89,92
-    else
-      CUDA_TRY(cudaMemsetAsync(b.dE_new, 0, (size_t)b.ne * sizeof(float4), st));
-    TRY(stage_end(b));
+
+    // ---- main: dS_{it+1} = ray-scatter(dJ_{it+1}) into the buffer that held dS_{it-1}
     snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
     TRY(stage_begin(b, name));
-    LAUNCH(launch_ray_scatter(P, b.he_begin, b.he_count, b.dJ, b.dS, b.counter + 1, st));  // :91,93
+    if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
+    float4 *ds_next = dsbuf[(it + 1) & 1];
+    LAUNCH(launch_ray_scatter(P, b.he_begin, b.he_count, b.dJ, ds_next, b.counter + 1, st));  // :91,93
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_ray_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
-    TRY(gather(b, b.dS));
+    TRY(gather(b, ds_next));
     TRY(stage_end(b));
-    snprintf(name, sizeof name, "iter%d_accumulate", it + 1);
-    TRY(stage_begin(b, name));
-    std::swap(b.dE, b.dE_new);
-    LAUNCH(launch_resample_2d(P, 1, it == 0 ? nullptr : b.Eacc, b.dE, b.Eacc_new, nullptr, st));  // :94-95
-    std::swap(b.Eacc, b.Eacc_new);
-    LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, b.dS, b.S_new, nullptr, st));        // :96-97
+    ds = SSource{ds_next, nullptr, 0.0};
+  }
+
+  // ---- side: last accumulation and the file-layout tables; main joins
+  TRY(stage_begin(b, "final_accumulate_and_files"));
+  TRY(order_after(b, ev, st, side));
+  if (N == 0) {
+    CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
+    CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), side));       // :76 E = 0
+    e_cur = b.Eacc;
+    LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, side));   // :101,105
+  } else {
+    LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, ds.tab_a, b.S_new, nullptr, side));  // :96-97 (last order)
     std::swap(b.S, b.S_new);
     s_cur = b.S;
-    ds = SSource{b.dS, nullptr, 0.0};
-    TRY(stage_end(b));
   }
-  TRY(stage_begin(b, "final_resample"));
-  LAUNCH(launch_resample_2d(P, 2, b.T, nullptr, nullptr, b.file_T, st));              // :98,102
-  LAUNCH(launch_resample_2d(P, 1, b.Eacc, nullptr, nullptr, b.file_E, st));           // :99,103
-  LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, nullptr, nullptr, b.file_S, st));      // :100,104
-  LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, st));       // :101,105
+  LAUNCH(launch_resample_2d(P, 1, e_cur, nullptr, nullptr, b.file_E, side));          // :99,103
+  LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, nullptr, nullptr, b.file_S, side));    // :100,104
+  TRY(order_after(b, ev, side, st));
   TRY(stage_end(b));
   b.ran = true;
   return 0;
@@ -706,8 +780,8 @@ extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atm
   float4 *ta = nullptr, *tb = nullptr;
   const size_t tile_count = (size_t)P.shapes.s4[0] * w.size() * P.shapes.s4[2] * P.shapes.s4[3];
   if (d.alloc(ta, tile_count) || (b && d.alloc(tb, tile_count))) return 1;
-  CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), ta, g_stream));
-  if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), tb, g_stream));
+  CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), 0, P.shapes.s4[0], ta, g_stream));
+  if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), 0, P.shapes.s4[0], tb, g_stream));
   CUDA_TRY(launch_point_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
                                 ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info, o,
                                 g_stream));

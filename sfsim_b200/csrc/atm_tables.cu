@@ -422,10 +422,11 @@ __global__ void k_point_scatter_prepare(Params P, const double *__restrict__ dir
 // tiles[(h * ndirs + d)][s][a] = mix_h(mix_e(tab)); the point-scatter kernel then interpolates the two
 // remaining axes inside one 4 KB tile (4 loads per lookup instead of 16, shared by 127 CTAs).
 __global__ void __launch_bounds__(256) k_blend_dir_tiles(Params P, const float4 *__restrict__ tab,
-                                                         const DirInfo *__restrict__ info, int ndirs, float4 *tiles) {
+                                                         const DirInfo *__restrict__ info, int ndirs, int h_first,
+                                                         float4 *tiles) {
   const int H = P.shapes.s4[0], E = P.shapes.s4[1];
   const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
-  const int hd = blockIdx.x;
+  const int hd = h_first * ndirs + blockIdx.x;
   const int h = hd / ndirs;
   const V3 x = index_to_height(P.planet, H, (double)h);
   const Axis ah = axis_from(height_to_index(P.planet, H, x), H);
@@ -785,9 +786,10 @@ cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, in
   return cudaGetLastError();
 }
 
-cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, float4 *tiles,
-                                   cudaStream_t st) {
-  k_blend_dir_tiles<<<P.shapes.s4[0] * ndirs, 256, 0, st>>>(P, tab, info, ndirs, tiles);
+cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, int h_first,
+                                   int h_count, float4 *tiles, cudaStream_t st) {
+  if (h_count <= 0) return cudaSuccess;
+  k_blend_dir_tiles<<<h_count * ndirs, 256, 0, st>>>(P, tab, info, ndirs, h_first, tiles);
   return cudaGetLastError();
 }
 

@@ -50,8 +50,9 @@ cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, cons
                                unsigned long long *counter, cudaStream_t st);
 cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
                                          cudaStream_t st);
-cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, float4 *tiles,
-                                   cudaStream_t st);
+// blends the tiles of height indices [h_first, h_first + h_count)
+cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, int h_first,
+                                   int h_count, float4 *tiles, cudaStream_t st);
 // tiles_a / tiles_b: blended [height][direction][light-elevation][heading] tiles of the S source
 cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
