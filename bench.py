@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=24576, help="texels per stage in the CPU baseline sample")
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: p2p = kernels store into all GPUs' tables over NVLink + flag barrier; "
+                         "nccl = contiguous slabs + one NCCL all-gather per table")
     ap.add_argument("--workload", default="shipped", choices=["shipped", "stress"],
                     help="shipped = BASELINE.json configs[2] (the headline); stress = configs[4]: 4-D table at 2x "
                          "resolution per axis (64x253x64x16), 10 iterations")
@@ -214,7 +217,7 @@ def run_b200(args):
         cfg = _lib.make_config(ray_scatter_shape=(64, 253, 64, 16), iterations=10)
         workload = "stress: 4-D 64x253x64x16 (2x shipped per axis), T 64x255, E 16x63, ray-steps 100, sphere-steps 15, " \
                    "10 iterations, Earth defaults"
-    builder = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world)
+    builder = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world, mode=args.mode)
     stream = torch.cuda.ExternalStream(lib.atmlut_stream())
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -319,7 +322,7 @@ def run_b200(args):
                 "data": "synthetic", "build_time_s": ms_per_step * 1e-3,
                 "config": {"workload": workload, "l2": "512 MiB flush write between timed steps",
                            "timing": "CUDA events per step on the library stream, max over ranks",
-                           "parallelism": "slab%d" % world, "wall_s_timed_region": t_wall},
+                           "parallelism": ("single" if world == 1 else "%s%d" % (builder.mode, world)), "wall_s_timed_region": t_wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "stage_ms": {k: round(v, 4) for k, v in stage_dict.items()},
                 "work_per_step": work, "roofline": roofline}

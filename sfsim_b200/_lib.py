@@ -56,7 +56,8 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 EXPORTS = [
     "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate",
-    "atmlut_builder_create", "atmlut_slab", "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
+    "atmlut_builder_create", "atmlut_slab", "atmlut_builder_ipc_export", "atmlut_builder_ipc_import",
+    "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
     "atmlut_builder_download", "atmlut_builder_stage_count", "atmlut_builder_stage_name", "atmlut_builder_stage_ms",
     "atmlut_builder_work", "atmlut_builder_counter", "atmlut_builder_destroy",
     "atmlut_transmittance_table", "atmlut_surface_radiance_base_table", "atmlut_first_order_tables",
@@ -93,6 +94,8 @@ def load():
                      "atmlut_builder_stage_count"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.atmlut_builder_download.argtypes = [C.c_void_p] * 5
+        lib.atmlut_builder_ipc_export.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.atmlut_builder_ipc_import.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.atmlut_builder_stage_ms.argtypes = [C.c_void_p, C.c_int, c_float_p]
         lib.atmlut_builder_work.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
         lib.atmlut_builder_counter.argtypes = [C.c_void_p, C.c_int, c_double_p]

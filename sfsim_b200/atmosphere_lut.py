@@ -68,11 +68,14 @@ def generate_atmosphere_luts(out_dir="data/atmosphere", planet=earth, scatter=(m
 
 
 class AtmosphereLutBuilder:
-    """Device-resident build.  With world > 1 each rank computes a contiguous slab of every 4-D table and
-    the tables are reassembled with one all-gather each through torch.distributed (NCCL on GPUs)."""
+    """Device-resident build.  With world > 1 the 4-D tables are sharded over the ranks (one process per GPU):
+
+    * mode "p2p" (default on GPUs): ranks exchange CUDA IPC handles once through torch.distributed, the kernels
+      store every finished texel straight into all GPUs' tables over NVLink and a flag barrier closes each table;
+    * mode "nccl": each rank fills a contiguous slab and torch.distributed all-gathers every table (NCCL)."""
 
     def __init__(self, planet=earth, scatter=(mie, rayleigh), cfg=None, rank=0, world=1, device=None,
-                 process_group=None):
+                 process_group=None, mode="p2p"):
         self.lib = _lib.load()
         self.cfg = cfg or _lib.default_config()
         self.rank, self.world = rank, world
@@ -85,8 +88,23 @@ class AtmosphereLutBuilder:
                                              C.byref(self.handle)))
         self._callback = None
         self.gathers = 0
+        self.mode = mode if world > 1 else "single"
         if world > 1:
-            self._install_allgather(process_group)
+            if mode == "p2p":
+                self._exchange_ipc_handles(process_group)
+            elif mode == "nccl":
+                self._install_allgather(process_group)
+            else:
+                raise ValueError("mode must be 'p2p' or 'nccl'")
+
+    def _exchange_ipc_handles(self, process_group):
+        import torch.distributed as dist
+        mine = C.create_string_buffer(6 * 64)
+        check(self.lib.atmlut_builder_ipc_export(self.handle, mine, len(mine)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(mine.raw), group=process_group)
+        check(self.lib.atmlut_builder_ipc_import(self.handle, b"".join(everyone), self.world))
+        dist.barrier(group=process_group)
 
     def _install_allgather(self, process_group):
         import torch

@@ -149,6 +149,15 @@ struct Builder {
   float4 *T = nullptr, *dE = nullptr, *dE_new = nullptr, *Eacc = nullptr, *Eacc_new = nullptr;
   float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dS2 = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
   cudaStream_t side = nullptr;             // second stream of the build DAG
+  // peer-to-peer mode: every sharded table also mapped on the peers (CUDA IPC), flag words for the barrier
+  bool p2p = false;
+  int he_stride = 1;
+  PeerOut peer_R1 = {}, peer_M1 = {}, peer_dJ = {}, peer_dS = {}, peer_dS2 = {};
+  unsigned *flags = nullptr;
+  int *error_flag = nullptr;
+  unsigned *peer_flags[kMaxPeers] = {};
+  unsigned epoch = 0;
+  std::vector<void *> ipc_opened;
   std::vector<cudaEvent_t> events;         // ordering events between the two streams
   float *file_T = nullptr, *file_E = nullptr, *file_S = nullptr, *file_M = nullptr;
   double *sphere_dirs = nullptr, *sphere_w = nullptr, *half_dirs = nullptr, *half_w = nullptr;
@@ -174,6 +183,9 @@ struct Builder {
       cudaEventDestroy(s.end);
     }
     for (auto e : events) cudaEventDestroy(e);
+    for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (flags) cudaFree(flags);
+    if (error_flag) cudaFree(error_flag);
     if (side) cudaStreamDestroy(side);
   }
 };
@@ -223,6 +235,14 @@ static int builder_alloc(Builder &b) {
   if (dev_alloc(b.file_S, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.file_M, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.counter, 2)) return 1;
+  if (dev_alloc(b.flags, kMaxPeers) || dev_alloc(b.error_flag, 1)) return 1;
+  CUDA_TRY(cudaMemsetAsync(b.flags, 0, kMaxPeers * sizeof(unsigned), g_stream));
+  CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), g_stream));
+  b.peer_R1 = local_out(b.R1);
+  b.peer_M1 = local_out(b.M1);
+  b.peer_dJ = local_out(b.dJ);
+  b.peer_dS = local_out(b.dS);
+  b.peer_dS2 = local_out(b.dS2);
   std::vector<double> dirs, w;
   sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);  // sphere.clj:102-105
   b.n_sphere = (int)w.size();
@@ -257,8 +277,17 @@ static int stage_end(Builder &b) {
   return 0;
 }
 
+static int peer_barrier(Builder &b) {
+  b.epoch++;
+  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, b.rank, b.world, b.epoch, b.error_flag, g_stream));
+  b.launches++;
+  return 0;
+}
+
 static int gather(Builder &b, float4 *table) {
-  if (b.world <= 1 || !b.allgather) return 0;
+  if (b.world <= 1) return 0;
+  if (b.p2p) return peer_barrier(b);   // the kernel already stored this rank's texels on every GPU
+  if (!b.allgather) return 0;
   size_t bytes = (size_t)b.he_per_rank * b.ntex * sizeof(float4);
   if (b.allgather(b.allgather_user, table, bytes, (void *)g_stream)) return fail("allgather callback failed");
   return 0;
@@ -310,13 +339,18 @@ static int builder_run(Builder &b) {
   b.launches = 0;
   size_t ev = 0;
   const int E = P.shapes.s4[1];
-  const int h_first = b.he_count > 0 ? b.he_begin / E : 0;
-  const int h_count = b.he_count > 0 ? (b.he_begin + b.he_count - 1) / E - h_first + 1 : 0;
+  const Shard shard = {b.he_begin, b.he_stride};
+  // heights whose direction tiles this rank needs: its slab's rows, or all of them when pairs are interleaved
+  const int h_first = (b.he_count > 0 && !b.p2p) ? b.he_begin / E : 0;
+  const int h_count = b.he_count <= 0 ? 0 : (b.p2p ? P.shapes.s4[0] : (b.he_begin + b.he_count - 1) / E - h_first + 1);
   float4 *dsbuf[2] = {b.dS, b.dS2};
+  const PeerOut dsout[2] = {b.peer_dS, b.peer_dS2};
   float4 *debuf[2] = {b.dE, b.dE_new};
   const int N = b.iterations;
 
   CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
+  // peer-to-peer mode: nobody may store into a peer's tables before that peer has finished its previous run
+  if (b.p2p && b.world > 1) TRY(peer_barrier(b));
   TRY(order_after(b, ev, st, side));   // the side stream starts after whatever the main stream did before
 
   // ---- side: 2-D tables and per-direction constants
@@ -331,9 +365,9 @@ static int builder_run(Builder &b) {
 
   // ---- main: first order
   TRY(stage_begin(b, "first_order"));
-  FirstOrderOut rayleigh = {b.R1, 1, 0};                                              // :68,71,77
-  FirstOrderOut mie_strength = {b.M1, 0, 1};                                          // :69,72,78
-  LAUNCH(launch_first_order(P, b.he_begin, b.he_count, rayleigh, mie_strength, b.counter, st));
+  FirstOrderOut rayleigh = {b.peer_R1, 1, 0};                                         // :68,71,77
+  FirstOrderOut mie_strength = {b.peer_M1, 0, 1};                                     // :69,72,78
+  LAUNCH(launch_first_order(P, shard, b.he_count, rayleigh, mie_strength, b.counter, st));
   TRY(stage_end(b));
   TRY(stage_begin(b, "first_order_allgather"));
   TRY(gather(b, b.R1));
@@ -380,8 +414,11 @@ static int builder_run(Builder &b) {
       LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_a, st));
       if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_b, st));
     }
-    LAUNCH(launch_point_scatter(P, b.he_begin, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
-                                debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.dJ, st));  // :88,90
+    LAUNCH(launch_point_scatter(P, shard, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
+                                debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.peer_dJ, st));  // :88,90
+    // the next ray-scatter overwrites the buffer of dS_{it-1} (on every GPU in peer-to-peer mode): this
+    // rank's side stream must be done reading it before the barrier / all-gather below lets anyone go on
+    if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_point_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
@@ -391,9 +428,8 @@ static int builder_run(Builder &b) {
     // ---- main: dS_{it+1} = ray-scatter(dJ_{it+1}) into the buffer that held dS_{it-1}
     snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
     TRY(stage_begin(b, name));
-    if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
     float4 *ds_next = dsbuf[(it + 1) & 1];
-    LAUNCH(launch_ray_scatter(P, b.he_begin, b.he_count, b.dJ, ds_next, b.counter + 1, st));  // :91,93
+    LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.dJ, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_ray_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
@@ -522,6 +558,61 @@ extern "C" int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *co
   return 0;
 }
 
+// ---- peer-to-peer mode: CUDA IPC handles of the sharded tables and the barrier flags ----
+static const int kIpcTables = 6;   // R1, M1, dJ, dS, dS2, flags
+
+extern "C" int atmlut_builder_ipc_export(void *builder, unsigned char *handles, int capacity_bytes) {
+  Builder *b = (Builder *)builder;
+  if (!b || !handles) return fail("invalid argument");
+  if (capacity_bytes < kIpcTables * (int)sizeof(cudaIpcMemHandle_t)) return fail("handle buffer too small");
+  void *ptrs[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->flags};
+  for (int i = 0; i < kIpcTables; i++) {
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ptrs[i]));
+    memcpy(handles + i * sizeof h, &h, sizeof h);
+  }
+  return 0;
+}
+
+extern "C" int atmlut_builder_ipc_import(void *builder, const unsigned char *all_handles, int world) {
+  Builder *b = (Builder *)builder;
+  if (!b || !all_handles) return fail("invalid argument");
+  if (world != b->world) return fail("world size mismatch");
+  if (world > kMaxPeers) return fail("peer-to-peer mode supports at most 8 GPUs");
+  if (b->p2p) return fail("peer handles were already imported");
+  PeerOut *outs[5] = {&b->peer_R1, &b->peer_M1, &b->peer_dJ, &b->peer_dS, &b->peer_dS2};
+  for (int q = 0; q < world; q++) {
+    void *ptrs[kIpcTables];
+    if (q == b->rank) {
+      void *mine[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->flags};
+      memcpy(ptrs, mine, sizeof mine);
+    } else {
+      for (int i = 0; i < kIpcTables; i++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + ((size_t)q * kIpcTables + i) * sizeof h, sizeof h);
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+        b->ipc_opened.push_back(ptrs[i]);
+      }
+      for (int i = 0; i < 5; i++) outs[i]->p[outs[i]->n++] = (float4 *)ptrs[i];
+    }
+    b->peer_flags[q] = (unsigned *)ptrs[5];
+  }
+  // interleaved pairs: rank r integrates pairs r, r + world, ... (balances cost; no layout constraint here)
+  b->p2p = true;
+  b->he_stride = world;
+  b->he_begin = b->rank;
+  b->he_count = b->n_he > b->rank ? (b->n_he - b->rank + world - 1) / world : 0;
+  return 0;
+}
+
+static int check_peer_error(Builder *b) {
+  if (!b->p2p) return 0;
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, b->error_flag, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) return fail("peer barrier timed out: a peer GPU never arrived");
+  return 0;
+}
+
 extern "C" int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *user) {
   if (!builder) return fail("builder is NULL");
   Builder *b = (Builder *)builder;
@@ -533,13 +624,14 @@ extern "C" int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn f
 extern "C" int atmlut_builder_run(void *builder) {
   if (!builder) return fail("builder is NULL");
   Builder *b = (Builder *)builder;
-  if (b->world > 1 && !b->allgather) return fail("world > 1 needs an allgather callback");
+  if (b->world > 1 && !b->allgather && !b->p2p)
+    return fail("world > 1 needs an allgather callback or imported peer handles");
   return builder_run(*b);
 }
 
 extern "C" int atmlut_builder_sync(void *builder) {
-  (void)builder;
   CUDA_TRY(cudaStreamSynchronize(g_stream));
+  if (builder) return check_peer_error((Builder *)builder);
   return 0;
 }
 
@@ -557,7 +649,7 @@ extern "C" int atmlut_builder_download(void *builder, float *transmittance, floa
   if (mie_strength)
     CUDA_TRY(cudaMemcpyAsync(mie_strength, b->file_M, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, g_stream));
   CUDA_TRY(cudaStreamSynchronize(g_stream));
-  return 0;
+  return check_peer_error(b);
 }
 
 extern "C" int atmlut_builder_stage_count(void *builder) {
@@ -590,8 +682,10 @@ extern "C" int atmlut_builder_work(void *builder, double *esamples, double *look
   const Params &P = b->P;
   const double steps = P.shapes.ray_steps;
   double surf_dirs = 0;  // surface-hitting directions summed over this rank's (height, elevation) pairs
-  for (int he = b->he_begin; he < b->he_begin + b->he_count; he++)
+  for (int i = 0; i < b->he_count; i++) {
+    const int he = b->he_begin + i * b->he_stride;
     for (int d = 0; d < b->n_sphere; d++) surf_dirs += info[(size_t)(he / P.shapes.s4[1]) * b->n_sphere + d].surface;
+  }
   double surf_hd = 0;
   for (auto &i : info) surf_hd += i.surface;
   const double slab = (double)b->he_count * b->ntex;
@@ -748,8 +842,8 @@ extern "C" int atmlut_first_order_tables(const atmlut_planet *planet, const atml
   const long long n4 = n4_of(P);
   if (out_a && d.alloc(ta, (size_t)n4)) return 1;
   if (out_b && d.alloc(tb, (size_t)n4)) return 1;
-  FirstOrderOut oa = {ta, component_a, strength_a}, ob = {tb, component_b, strength_b};
-  CUDA_TRY(launch_first_order(P, 0, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
+  FirstOrderOut oa = {local_out(ta), component_a, strength_a}, ob = {local_out(tb), component_b, strength_b};
+  CUDA_TRY(launch_first_order(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
   if (out_a && d.download_rgb(ta, n4, out_a)) return 1;
   if (out_b && d.download_rgb(tb, n4, out_b)) return 1;
   CUDA_TRY(cudaStreamSynchronize(g_stream));
@@ -782,9 +876,9 @@ extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atm
   if (d.alloc(ta, tile_count) || (b && d.alloc(tb, tile_count))) return 1;
   CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), 0, P.shapes.s4[0], ta, g_stream));
   if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), 0, P.shapes.s4[0], tb, g_stream));
-  CUDA_TRY(launch_point_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
-                                ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info, o,
-                                g_stream));
+  CUDA_TRY(launch_point_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
+                                ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info,
+                                local_out(o), g_stream));
   return d.download_rgb(o, n4, out);
 }
 
@@ -824,7 +918,7 @@ extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlu
   const long long n4 = n4_of(P);
   float4 *j = nullptr, *o = nullptr;
   if (d.upload_rgb(dj, n4, j) || d.alloc(o, (size_t)n4)) return 1;
-  CUDA_TRY(launch_ray_scatter(P, 0, P.shapes.s4[0] * P.shapes.s4[1], j, o, nullptr, g_stream));
+  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, local_out(o), nullptr, g_stream));
   return d.download_rgb(o, n4, out);
 }
 

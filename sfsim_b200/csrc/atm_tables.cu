@@ -98,6 +98,11 @@ __device__ void setup_view_ray(const Params &P, int h, int e, ViewSmem &vs, unsi
   __syncthreads();
 }
 
+__device__ __forceinline__ void store_all(const PeerOut &o, size_t idx, float4 v) {
+#pragma unroll 1
+  for (int q = 0; q < o.n; q++) o.p[q][idx] = v;
+}
+
 __device__ __forceinline__ void count_esamples(unsigned long long *counter, unsigned n) {
   if (!counter) return;
   n = (unsigned)__reduce_add_sync(0xffffffffu, n);
@@ -191,7 +196,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
   FirstOrderOut outs[2] = {oa, ob};
 #pragma unroll
   for (int o = 0; o < 2; o++) {
-    if (!outs[o].table) continue;
+    if (outs[o].out.n == 0) continue;
     const int c = outs[o].component;
     const float *acc = c ? acc1 : acc0;
     const double ph = outs[o].strength ? 1.0 : phase(P.medium.g[c], mu);
@@ -200,7 +205,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
     val.y = (float)(P.medium.base[c][1] * ph * P.intensity[1] * a * (double)acc[1]);
     val.z = (float)(P.medium.base[c][2] * ph * P.intensity[2] * a * (double)acc[2]);
     val.w = 0.0f;
-    outs[o].table[idx] = val;
+    store_all(outs[o].out, idx, val);
   }
 }
 
@@ -211,7 +216,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
-__global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int kparts, int passes, int nchunks,
+__global__ void __launch_bounds__(256) k_first_order(Params P, Shard shard, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
                                                      unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(256) k_first_order(Params P, int he_begin, int
   float *partial = reinterpret_cast<float *>(smem_raw + sizeof(ViewSmem));  // [6][blockDim] when kparts > 1
   const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int ntex = S * A;
-  const int he = he_begin + blockIdx.x / nchunks;
+  const int he = shard.begin + (blockIdx.x / nchunks) * shard.stride;
   const int chunk = blockIdx.x % nchunks;
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
@@ -299,14 +304,14 @@ struct alignas(16) LookupSmem {
 // corner tiles of dJ into one [light-elevation][heading] tile in shared memory (coalesced float4
 // loads, double buffered), and each texel then interpolates inside that tile: 4 shared-memory loads
 // per lookup instead of 16 scattered global ones.
-__global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, const float4 *__restrict__ dj,
-                                                      float4 *out, unsigned long long *counter) {
+__global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, const float4 *__restrict__ dj,
+                                                      PeerOut out, unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
   LookupSmem &ls = *reinterpret_cast<LookupSmem *>(smem_raw + sizeof(ViewSmem));
   float4 *tiles = reinterpret_cast<float4 *>(smem_raw + sizeof(ViewSmem) + sizeof(LookupSmem));
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
-  const int he = he_begin + blockIdx.x;
+  const int he = shard.begin + blockIdx.x * shard.stride;
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, int he_begin, co
         acc[2] = fmaf(ls.tr[k][2], j.z, acc[2]);
       }
     }
-    if (active) out[(size_t)he * ntex + texel] = make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f);
+    if (active) store_all(out, (size_t)he * ntex + texel, make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f));
     __syncthreads();
   }
   count_esamples(counter, esamples);
@@ -451,17 +456,17 @@ struct alignas(16) PointDir {
 };
 
 // dJ[i] = integral-sphere of overall-in-scattering * (S(x, omega, l, not surface) + surface term)
-__global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, const float4 *__restrict__ tiles_a,
+__global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, const float4 *__restrict__ tiles_a,
                                                        const float4 *__restrict__ tiles_b, double phase_g,
                                                        const float4 *__restrict__ de,
                                                        const double *__restrict__ dirs,
                                                        const double *__restrict__ weights, int ndirs,
-                                                       const DirInfo *__restrict__ info, float4 *out) {
+                                                       const DirInfo *__restrict__ info, PeerOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PointDir *pd = reinterpret_cast<PointDir *>(smem_raw);
   __shared__ double s_geom[4];
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
-  const int he = he_begin + blockIdx.x;
+  const int he = shard.begin + blockIdx.x * shard.stride;
   const int h = he / E, e = he % E;
   if (threadIdx.x == 0) {
     V3 x = index_to_height(P.planet, H, (double)h);
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, int he_begin, c
       acc[1] = fmaf(r.sc[1], s.y, acc[1]);
       acc[2] = fmaf(r.sc[2], s.z, acc[2]);
     }
-    out[(size_t)he * ntex + texel] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+    store_all(out, (size_t)he * ntex + texel, make_float4(acc[0], acc[1], acc[2], 0.0f));
   }
 }
 
@@ -715,6 +720,36 @@ __global__ void k_float4_to_rgb(const float4 *in, float *out, long long n) {
   }
 }
 
+// ------------------------------------------------------------------ cross-GPU barrier (peer-to-peer mode)
+
+struct PeerFlags {
+  unsigned *p[kMaxPeers];
+};
+
+// Thread q signals `epoch` into flag word [rank] of GPU q and then waits until GPU q has signalled this
+// GPU.  The kernels whose stores must be visible ran earlier on the same stream; the system-scope fence
+// orders them before the flag.  Epochs only grow, so a GPU that runs ahead never confuses a slower one.
+// A peer that never arrives (crashed process) trips the clock-based timeout instead of hanging the box.
+__global__ void k_peer_barrier(unsigned *local_flags, PeerFlags peers, int rank, int world, unsigned epoch,
+                               int *error_flag) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  __threadfence_system();
+  volatile unsigned *remote = peers.p[q] + rank;
+  *remote = epoch;
+  __threadfence_system();
+  volatile unsigned *mine = local_flags + q;
+  const long long start = clock64();
+  while ((int)(*mine - epoch) < 0) {
+    if (clock64() - start > 20000000000LL) {   // about 10 s
+      atomicExch(error_flag, 1);
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
 // ------------------------------------------------------------------ launchers
 
 static int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -736,7 +771,7 @@ static int env_int(const char *name, int fallback) {
   return v && *v ? atoi(v) : fallback;
 }
 
-cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, FirstOrderOut oa, FirstOrderOut ob,
+cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
@@ -754,7 +789,7 @@ cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, Firs
     nchunks = (total_warps + warps - 1) / warps;
   }
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
-  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, he_begin, kparts, passes, nchunks, oa, ob, counter);
+  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);
   return cudaGetLastError();
 }
 
@@ -768,14 +803,14 @@ size_t ray_scatter_smem(const Params &P) {
   return sizeof(ViewSmem) + sizeof(LookupSmem) + 2 * (size_t)P.shapes.s4[2] * P.shapes.s4[3] * sizeof(float4);
 }
 
-cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, const float4 *dj, float4 *out,
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, PeerOut out,
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   size_t smem = ray_scatter_smem(P);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // light-elevation x heading tile too large
   cudaError_t e = cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, he_begin, dj, out, counter);
+  k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, out, counter);
   return cudaGetLastError();
 }
 
@@ -793,15 +828,15 @@ cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const Dir
   return cudaGetLastError();
 }
 
-cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, const float4 *tiles_a,
+cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
-                                 const double *weights, int ndirs, const DirInfo *info, float4 *out,
+                                 const double *weights, int ndirs, const DirInfo *info, PeerOut out,
                                  cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   size_t smem = (size_t)ndirs * sizeof(PointDir);
   cudaError_t e = cudaFuncSetAttribute(k_point_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_point_scatter<<<he_count, 256, smem, st>>>(P, he_begin, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info,
+  k_point_scatter<<<he_count, 256, smem, st>>>(P, shard, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info,
                                                out);
   return cudaGetLastError();
 }
@@ -832,6 +867,14 @@ cudaError_t launch_resample_2d(const Params &P, int which, const float4 *a, cons
   const int *shape = which == 1 ? P.shapes.se : P.shapes.st;
   int n = shape[0] * shape[1];
   k_resample_2d<<<div_up(n, 128), 128, 0, st>>>(P, which, a, b, out, file_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int rank, int world,
+                                unsigned epoch, int *error_flag, cudaStream_t st) {
+  PeerFlags f = {};
+  for (int q = 0; q < world && q < kMaxPeers; q++) f.p[q] = peer_flags[q];
+  k_peer_barrier<<<1, 32, 0, st>>>(local_flags, f, rank, world, epoch, error_flag);
   return cudaGetLastError();
 }
 

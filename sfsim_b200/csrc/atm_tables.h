@@ -9,10 +9,34 @@ namespace atm {
 
 constexpr int kMaxDirs = 1536;  // sphere quadrature directions the point-scatter kernel keeps in shared memory
 
+constexpr int kMaxPeers = 8;    // GPUs of one NVSwitch box
+
+// Which (height, elevation) pairs a launch integrates: CTA i owns pair begin + i * stride.
+// stride 1 = contiguous slab (NCCL all-gather reassembles the table); stride = world = interleaved pairs
+// (peer-to-peer mode: results are stored straight into every GPU's table, so no layout constraint).
+struct Shard {
+  int begin, stride;
+};
+
+// One logical output table: the local copy (p[0]) and the same table on the peer GPUs, mapped through
+// CUDA IPC.  Kernels store each finished texel to all of them (16-byte posted writes over NVLink), which
+// overlaps the "all-gather" with the integration itself.
+struct PeerOut {
+  float4 *p[kMaxPeers];
+  int n;   // 0 = output not wanted
+};
+
+inline PeerOut local_out(float4 *table) {
+  PeerOut o = {};
+  o.p[0] = table;
+  o.n = table ? 1 : 0;
+  return o;
+}
+
 // one output of the first-order kernel: ray-scatter of point-scatter-component (strength = 0) or
 // strength-component (strength = 1) of scatter[component]
 struct FirstOrderOut {
-  float4 *table;
+  PeerOut out;
   int component;
   int strength;
 };
@@ -44,19 +68,22 @@ struct HalfDirInfo {
 
 cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_t st);
 cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st);
-cudaError_t launch_first_order(const Params &P, int he_begin, int he_count, FirstOrderOut oa, FirstOrderOut ob,
+cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
                                unsigned long long *counter, cudaStream_t st);
-cudaError_t launch_ray_scatter(const Params &P, int he_begin, int he_count, const float4 *dj, float4 *out,
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, PeerOut out,
                                unsigned long long *counter, cudaStream_t st);
+// cross-GPU barrier over peer-mapped flag words: signal `epoch` to every peer, wait for every peer's signal
+cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int rank, int world,
+                                unsigned epoch, int *error_flag, cudaStream_t st);
 cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
                                          cudaStream_t st);
 // blends the tiles of height indices [h_first, h_first + h_count)
 cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, int h_first,
                                    int h_count, float4 *tiles, cudaStream_t st);
 // tiles_a / tiles_b: blended [height][direction][light-elevation][heading] tiles of the S source
-cudaError_t launch_point_scatter(const Params &P, int he_begin, int he_count, const float4 *tiles_a,
+cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
-                                 const double *weights, int ndirs, const DirInfo *info, float4 *out,
+                                 const double *weights, int ndirs, const DirInfo *info, PeerOut out,
                                  cudaStream_t st);
 size_t ray_scatter_smem(const Params &P);
 cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,

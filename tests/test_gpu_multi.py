@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("extra", [["--reduced"], []])
+@pytest.mark.parametrize("extra", [["--reduced"], [], ["--reduced", "--mode", "nccl"], ["--mode", "nccl"]])
 def test_sharded_build_is_identical(extra):
     import torch
     n = torch.cuda.device_count()

@@ -19,6 +19,8 @@ from sfsim_b200 import _lib, atmosphere_lut  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reduced", action="store_true", help="4-D [5,7,8,2]: pair count not divisible by the world size")
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--repeat", type=int, default=3, help="builds in a row (exercises buffer reuse across runs)")
     args = ap.parse_args()
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -30,8 +32,9 @@ def main():
                                ray_steps=20, sphere_steps=8, iterations=2)
     else:
         cfg = _lib.default_config()
-    sharded = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world)
-    sharded.run()
+    sharded = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world, mode=args.mode)
+    for _ in range(args.repeat):
+        sharded.run()
     sharded.sync()
     got = sharded.download()
     gathers = sharded.gathers
@@ -49,7 +52,7 @@ def main():
             ok = ok and same
             print("%-26s %s" % (name, "identical" if same else "DIFFERENT (max abs %.3g)" % float(np.abs(g - w).max())))
         print("all-gathers per build: %d" % gathers)
-        print("MULTI_GPU_CHECK %s world=%d" % ("OK" if ok else "FAILED", world))
+        print("MULTI_GPU_CHECK %s world=%d mode=%s" % ("OK" if ok else "FAILED", world, args.mode))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
