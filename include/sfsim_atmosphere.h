@@ -153,6 +153,23 @@ int atmlut_ray_scatter_first_order_batch(const atmlut_planet *planet, const atml
                                          const double *x, const double *v, const double *l, const int *above,
                                          double *out);
 
+/* The same three integrals with TABLE sources at arbitrary points: the functions the reference passes around
+ * as closures are interpolation-tables here (host float RGB tables, logical layout [..][3]).
+ * ray-scatter (atmosphere.clj:192-200) with point-scatter = interpolation-table of dj over point-scatter-space */
+int atmlut_ray_scatter_table_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                                   const int *shape4, const float *dj, int count, const double *x, const double *v,
+                                   const double *l, const int *above, double *out);
+/* point-scatter (atmosphere.clj:203-222); ray-scatter = ds_a [+ ds_b * phase(scatter[phase_component], v.l)],
+ * surface-radiance = interpolation-table of de over surface-radiance-space of shape_e */
+int atmlut_point_scatter_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int sphere_steps,
+                               int ray_steps, const int *shape4, const float *ds_a, const float *ds_b,
+                               int phase_component, const int *shape_e, const float *de, int count, const double *x,
+                               const double *v, const double *l, double *out);
+/* surface-radiance (atmosphere.clj:225-230) with the same kind of ray-scatter source */
+int atmlut_surface_radiance_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, int steps,
+                                  const int *shape4, const float *ds_a, const float *ds_b, int phase_component,
+                                  int count, const double *x, const double *l, double *out);
+
 /* ---- index maps (atmosphere.clj:233-422), evaluated on the device in double precision ---- */
 /* which: 0 = ray-scatter-space [4 indices; point, direction, light, above]
  *        1 = surface-radiance-space [2 indices; point, light]

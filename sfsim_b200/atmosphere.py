@@ -153,21 +153,81 @@ def point_scatter_base(planet, scatter, steps, intensity, x, view_direction, lig
     return FirstOrder(FirstOrder.BASE, planet, scatter, None, steps, intensity)(x, view_direction, light_direction)
 
 
+def _source_tables(src):
+    """(table a, table b or None, mie component or None) of a ray-scatter source: an InterpolationTable over
+    ray-scatter-space or the MieCombined closure of atmosphere_lut.clj:79-84."""
+    from . import interpolate
+    if isinstance(src, interpolate.MieCombined):
+        a = src.a.table if isinstance(src.a, interpolate.InterpolationTable) else src.a
+        b = src.b.table if isinstance(src.b, interpolate.InterpolationTable) else src.b
+        return _lib.f32(a), _lib.f32(b), src.mie
+    if isinstance(src, interpolate.InterpolationTable):
+        return _lib.f32(src.table), None, None
+    raise TypeError("expected an InterpolationTable or MieCombined source, got %r" % (src,))
+
+
 def ray_scatter(planet, scatter, steps, point_scatter, x, view_direction, light_direction, above_horizon):
-    """atmosphere.clj:192-200 with `point_scatter` a FirstOrder source."""
-    if not isinstance(point_scatter, FirstOrder):
-        raise TypeError("ray_scatter evaluates first-order sources (FirstOrder); table sources are integrated by "
-                        "make_lookup_table(RayScatter(...))")
+    """atmosphere.clj:192-200.  `point_scatter` is a FirstOrder source or an InterpolationTable over
+    point-scatter-space (the interpolated dJ of atmosphere_lut.clj:90-91)."""
     lib = _lib.load()
     x, v, l = _pts(x), _pts(view_direction), _pts(light_direction)
-    ab = _lib.i32(np.asarray([above_horizon], dtype=bool))
+    ab = _lib.i32(np.broadcast_to(np.asarray(above_horizon, dtype=bool), (len(x),)))
     out = np.zeros_like(x)
     pl = _lib.make_planet(planet)
     sc = _lib.make_scatter_array(scatter)
-    check(lib.atmlut_ray_scatter_first_order_batch(C.byref(pl), sc, len(scatter), point_scatter.kind,
-                                                   point_scatter.component, int(steps),
-                                                   _lib.vec3(point_scatter.intensity), len(x), _lib.ptr(x),
-                                                   _lib.ptr(v), _lib.ptr(l), _lib.ptr(ab), _lib.ptr(out)))
+    if isinstance(point_scatter, FirstOrder):
+        check(lib.atmlut_ray_scatter_first_order_batch(C.byref(pl), sc, len(scatter), point_scatter.kind,
+                                                       point_scatter.component, int(steps),
+                                                       _lib.vec3(point_scatter.intensity), len(x), _lib.ptr(x),
+                                                       _lib.ptr(v), _lib.ptr(l), _lib.ptr(ab), _lib.ptr(out)))
+    else:
+        dj, _, _ = _source_tables(point_scatter)
+        shape = (C.c_int * 4)(*dj.shape[:4])
+        check(lib.atmlut_ray_scatter_table_batch(C.byref(pl), sc, len(scatter), int(steps), shape, _lib.ptr(dj),
+                                                 len(x), _lib.ptr(x), _lib.ptr(v), _lib.ptr(l), _lib.ptr(ab),
+                                                 _lib.ptr(out)))
+    return out[0]
+
+
+def point_scatter(planet, scatter, ray_scatter, surface_radiance, intensity, sphere_steps, ray_steps, x,
+                  view_direction, light_direction, above_horizon=True):
+    """atmosphere.clj:203-222 with `ray_scatter` an InterpolationTable / MieCombined over ray-scatter-space and
+    `surface_radiance` an InterpolationTable over surface-radiance-space (intensity and above-horizon are
+    ignored, like the reference's underscored parameters)."""
+    lib = _lib.load()
+    x, v, l = _pts(x), _pts(view_direction), _pts(light_direction)
+    out = np.zeros_like(x)
+    a, b, mie = _source_tables(ray_scatter)
+    e_tab = _lib.f32(surface_radiance.table)
+    scatter = list(scatter)
+    phase_component = 0
+    if b is not None:
+        matches = [i for i, s in enumerate(scatter) if s is mie or s == mie]
+        if not matches:
+            raise ValueError("the Mie component of the source must be one of the scatter components")
+        phase_component = matches[0]
+    pl = _lib.make_planet(planet)
+    sc = _lib.make_scatter_array(scatter)
+    shape4 = (C.c_int * 4)(*a.shape[:4])
+    shape_e = (C.c_int * 2)(*e_tab.shape[:2])
+    check(lib.atmlut_point_scatter_batch(C.byref(pl), sc, len(scatter), int(sphere_steps), int(ray_steps), shape4,
+                                         _lib.ptr(a), _lib.ptr(b), phase_component, shape_e, _lib.ptr(e_tab), len(x),
+                                         _lib.ptr(x), _lib.ptr(v), _lib.ptr(l), _lib.ptr(out)))
+    return out[0]
+
+
+def surface_radiance(planet, ray_scatter, steps, x, light_direction):
+    """atmosphere.clj:225-230 with `ray_scatter` an InterpolationTable / MieCombined over ray-scatter-space."""
+    lib = _lib.load()
+    x, l = _pts(x), _pts(light_direction)
+    out = np.zeros_like(x)
+    a, b, mie = _source_tables(ray_scatter)
+    scatter = [mie] if b is not None else []
+    pl = _lib.make_planet(planet)
+    sc = _lib.make_scatter_array(scatter)
+    shape4 = (C.c_int * 4)(*a.shape[:4])
+    check(lib.atmlut_surface_radiance_batch(C.byref(pl), sc, len(scatter), int(steps), shape4, _lib.ptr(a), _lib.ptr(b),
+                                            0, len(x), _lib.ptr(x), _lib.ptr(l), _lib.ptr(out)))
     return out[0]
 
 

@@ -238,6 +238,201 @@ __global__ void k_interpolate(const float *table, int dims, int n0, int n1, int 
   }
 }
 
+// ------------------------------------------------------------------ table-source evaluators at arbitrary points
+
+// interpolate-value (interpolate.clj:87-98) on a packed RGB float table, coordinates in double
+__device__ void lookup_rgb(const float *table, const int *shape, int dims, const double *coords, double out[3]) {
+  int lo[4], hi[4];
+  double frac[4];
+  long long stride[4];
+  long long s = 3;
+  for (int d = dims - 1; d >= 0; d--) {
+    stride[d] = s;
+    s *= shape[d];
+  }
+  for (int d = 0; d < dims; d++) {
+    double c = fmin(fmax(coords[d], 0.0), (double)(shape[d] - 1));
+    double u = floor(c);
+    lo[d] = (int)u;
+    hi[d] = min(lo[d] + 1, shape[d] - 1);
+    frac[d] = c - u;
+  }
+  for (int ch = 0; ch < 3; ch++) {
+    double vals[16];
+    const int corners = 1 << dims;
+    for (int c = 0; c < corners; c++) {
+      long long off = ch;
+      for (int d = 0; d < dims; d++) off += (long long)(((c >> (dims - 1 - d)) & 1) ? hi[d] : lo[d]) * stride[d];
+      vals[c] = (double)table[off];
+    }
+    for (int d = dims - 1; d >= 0; d--)
+      for (int c = 0; c < (1 << d); c++) vals[c] = vals[2 * c] * (1 - frac[d]) + vals[2 * c + 1] * frac[d];
+    out[ch] = vals[0];
+  }
+}
+
+struct TableSource {   // S source: tab_a, or tab_a + tab_b * phase(g, v.l) (atmosphere_lut.clj:79-84)
+  const float *tab_a, *tab_b;
+  double phase_g;
+  int shape[4];
+};
+
+__device__ void s_source(const Planet &pl, const TableSource &src, V3 x, V3 v, V3 l, bool above, double out[3]) {
+  double idx[4];
+  ray_scatter_forward(pl, src.shape, x, v, l, above, idx);
+  lookup_rgb(src.tab_a, src.shape, 4, idx, out);
+  if (src.tab_b) {
+    double m[3];
+    lookup_rgb(src.tab_b, src.shape, 4, idx, m);
+    double ph = phase(src.phase_g, dot(v, l));
+    for (int ch = 0; ch < 3; ch++) out[ch] = out[ch] + m[ch] * ph;
+  }
+}
+
+__device__ __forceinline__ void warp_sum3(double acc[3]) {
+  for (int ch = 0; ch < 3; ch++)
+    for (int o = 16; o > 0; o >>= 1) acc[ch] += __shfl_xor_sync(0xffffffffu, acc[ch], o);
+}
+
+// ray-scatter (atmosphere.clj:192-200) with point-scatter = interpolation-table of dJ; one warp per item
+__global__ void k_ray_scatter_table_batch(Planet pl, Medium md, int steps, TableSource src, int count, const double *x,
+                                          const double *v, const double *l, const int *above, double *out) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= count) return;
+  V3 xi = load3(x, i), vi = load3(v, i), li = load3(l, i);
+  const bool ab = above[i] != 0;
+  V3 point = ab ? atmosphere_intersection(pl, xi, vi) : surface_intersection(pl, xi, vi);
+  V3 d = point - xi;
+  double stepsize = 1.0 / (double)steps;
+  double a = stepsize * mag(d);
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int k = lane; k < steps; k += 32) {
+    V3 p = xi + d * ((0.5 + (double)k) * stepsize);
+    double t[3], j[3];
+    transmittance_points(pl, md, steps, xi, p, t);
+    s_source(pl, src, p, vi, li, ab, j);
+    for (int ch = 0; ch < 3; ch++) acc[ch] += (t[ch] * j[ch]) * a;
+  }
+  warp_sum3(acc);
+  if (lane == 0) store3(out, i, acc);
+}
+
+// quaternion.clj:166-171 orthogonal, matrix.clj:207-213 oriented-matrix (rows n, o1, o2)
+__device__ void oriented_matrix(V3 n, V3 &o1, V3 &o2) {
+  double ax = fabs(n.x), ay = fabs(n.y), az = fabs(n.z);
+  V3 b = v3(1, 0, 0);
+  double best = ax;
+  if (ay < best) {
+    b = v3(0, 1, 0);
+    best = ay;
+  }
+  if (az < best) b = v3(0, 0, 1);
+  V3 c = v3(n.y * b.z - n.z * b.y, n.z * b.x - n.x * b.z, n.x * b.y - n.y * b.x);
+  double m = mag(c);
+  o1 = v3(c.x / m, c.y / m, c.z / m);
+  o2 = v3(n.y * o1.z - n.z * o1.y, n.z * o1.x - n.x * o1.z, n.x * o1.y - n.y * o1.x);
+}
+
+// rings of spherical-integral (sphere.clj:70-93), computed on the host: cos/sin theta, ring size, weight
+struct Ring {
+  double cos_theta, sin_theta, weight;   // weight = factor * 2 pi / ringsteps
+  int ringsteps, first;
+};
+
+__device__ V3 ring_direction(const Ring &r, int j, V3 n, V3 o1, V3 o2) {
+  double phi = 2 * kPi * ((0.5 + (double)j) / (double)r.ringsteps);
+  double xx = r.cos_theta, yy = r.sin_theta * cos(phi), zz = r.sin_theta * sin(phi);
+  return v3(n.x * xx + o1.x * yy + o2.x * zz, n.y * xx + o1.y * yy + o2.y * zz, n.z * xx + o1.z * yy + o2.z * zz);
+}
+
+// point-scatter (atmosphere.clj:203-222) with table sources; one warp per item, lanes over directions
+__global__ void k_point_scatter_batch(Planet pl, Medium md, int ray_steps, TableSource src, const float *de,
+                                      int e_rows, int e_cols, const Ring *rings, int nrings, int ndirs, int count,
+                                      const double *x, const double *v, const double *l, double *out) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= count) return;
+  V3 xi = load3(x, i), vi = load3(v, i), li = load3(l, i);
+  double m = mag(xi);
+  V3 n = v3(xi.x / m, xi.y / m, xi.z / m), o1, o2;
+  oriented_matrix(n, o1, o2);
+  const double hx = height(pl, xi);
+  const int e_shape[2] = {e_rows, e_cols};
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int d = lane; d < ndirs; d += 32) {
+    int r = 0;
+    while (r + 1 < nrings && rings[r + 1].first <= d) r++;
+    V3 omega = ring_direction(rings[r], d - rings[r].first, n, o1, o2);
+    V3 point = ray_extremity(pl, xi, omega);
+    bool surface = surface_point(pl, point);
+    double s[3];
+    s_source(pl, src, xi, omega, li, !surface, s);
+    if (surface) {
+      double idx[2], e[3], t[3];
+      surface_radiance_forward(pl, e_shape, point, li, idx);
+      lookup_rgb(de, e_shape, 2, idx, e);
+      transmittance_points(pl, md, ray_steps, xi, point, t);
+      for (int ch = 0; ch < 3; ch++) s[ch] = s[ch] + t[ch] * ((pl.brightness[ch] / kPi) * e[ch]);
+    }
+    double mu = dot(vi, omega);
+    for (int ch = 0; ch < 3; ch++) {
+      double sum = 0.0;
+      for (int c = 0; c < md.n; c++) {
+        double term = scattering(md, c, ch, hx) * phase(md.g[c], mu);
+        sum = (c == 0) ? term : sum + term;
+      }
+      acc[ch] += (sum * s[ch]) * rings[r].weight;
+    }
+  }
+  warp_sum3(acc);
+  if (lane == 0) store3(out, i, acc);
+}
+
+// surface-radiance (atmosphere.clj:225-230) with a table source; one warp per item
+__global__ void k_surface_radiance_batch(Planet pl, TableSource src, const Ring *rings, int nrings, int ndirs,
+                                         int count, const double *x, const double *l, double *out) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= count) return;
+  V3 xi = load3(x, i), li = load3(l, i);
+  double m = mag(xi);
+  V3 n = v3(xi.x / m, xi.y / m, xi.z / m), o1, o2;
+  oriented_matrix(n, o1, o2);
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int d = lane; d < ndirs; d += 32) {
+    int r = 0;
+    while (r + 1 < nrings && rings[r + 1].first <= d) r++;
+    V3 omega = ring_direction(rings[r], d - rings[r].first, n, o1, o2);
+    double s[3];
+    s_source(pl, src, xi, omega, li, true, s);
+    double f = dot(omega, n) * rings[r].weight;
+    for (int ch = 0; ch < 3; ch++) acc[ch] += s[ch] * f;
+  }
+  warp_sum3(acc);
+  if (lane == 0) store3(out, i, acc);
+}
+
+// host: ring table of spherical-integral (sphere.clj:70-93)
+std::vector<Ring> make_rings(int theta_steps, int phi_steps, double theta_range, int &ndirs) {
+  std::vector<Ring> rings;
+  const double delta2 = theta_range / (double)theta_steps / 2;
+  ndirs = 0;
+  for (int k = 0; k < theta_steps; k++) {
+    double theta = theta_range * ((0.5 + (double)k) / (double)theta_steps);
+    double factor = cos(theta - delta2) - cos(theta + delta2);
+    Ring r;
+    r.ringsteps = (int)ceil(sin(theta) * (double)phi_steps);
+    r.cos_theta = cos(theta);
+    r.sin_theta = sin(theta);
+    r.weight = factor * ((2 * kPi) / (double)r.ringsteps);
+    r.first = ndirs;
+    ndirs += r.ringsteps;
+    rings.push_back(r);
+  }
+  return rings;
+}
+
 struct Bufs {
   std::vector<void *> ptrs;
   ~Bufs() {
@@ -377,6 +572,104 @@ extern "C" int atmlut_ray_scatter_first_order_batch(const atmlut_planet *planet,
   k_ray_scatter_first_order_batch<<<blocks((long long)count * 32, 128), 128, 0, stream()>>>(
       P.planet, P.medium, kind, component, steps, v3(intensity[0], intensity[1], intensity[2]), count, dx, dv, dl, dab,
       dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+static int make_table_source(Bufs &b, const Params &P, const int *shape4, const float *ds_a, const float *ds_b,
+                             double phase_g, TableSource &src) {
+  size_t n = 3;
+  for (int i = 0; i < 4; i++) {
+    if (shape4[i] < 2) return fail("every table axis needs at least 2 entries");
+    src.shape[i] = shape4[i];
+    n *= (size_t)shape4[i];
+  }
+  float *da = nullptr, *db = nullptr;
+  if (b.up(ds_a, n, da) || (ds_b && b.up(ds_b, n, db))) return 1;
+  src.tab_a = da;
+  src.tab_b = db;
+  src.phase_g = phase_g;
+  (void)P;
+  return 0;
+}
+
+extern "C" int atmlut_ray_scatter_table_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                              int steps, const int *shape4, const float *dj, int count,
+                                              const double *x, const double *v, const double *l, const int *above,
+                                              double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 1 && count >= 0 && shape4 && dj && x && v && l && above && out, "invalid argument");
+  if (count == 0) return 0;
+  Bufs b;
+  TableSource src = {};
+  if (make_table_source(b, P, shape4, dj, nullptr, 0.0, src)) return 1;
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dv, *dl, *dout;
+  int *dab;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(v, (size_t)count * 3, dv) || b.up(l, (size_t)count * 3, dl) ||
+      b.up(above, (size_t)count, dab) || b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_ray_scatter_table_batch<<<blocks((long long)count * 32, 128), 128, 0, stream()>>>(P.planet, P.medium, steps, src,
+                                                                                      count, dx, dv, dl, dab, dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_point_scatter_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                          int sphere_steps, int ray_steps, const int *shape4, const float *ds_a,
+                                          const float *ds_b, int phase_component, const int *shape_e,
+                                          const float *de, int count, const double *x, const double *v,
+                                          const double *l, double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(sphere_steps >= 2 && ray_steps >= 1 && count >= 0 && shape4 && ds_a && shape_e && de && x && v && l && out,
+             "invalid argument");
+  CHECK_ARGS(!ds_b || (phase_component >= 0 && phase_component < n), "phase component out of range");
+  CHECK_ARGS(shape_e[0] >= 2 && shape_e[1] >= 2, "every table axis needs at least 2 entries");
+  if (count == 0) return 0;
+  Bufs b;
+  TableSource src = {};
+  if (make_table_source(b, P, shape4, ds_a, ds_b, ds_b ? P.medium.g[phase_component] : 0.0, src)) return 1;
+  int ndirs = 0;
+  std::vector<Ring> rings = make_rings(sphere_steps >> 1, sphere_steps, kPi, ndirs);   // sphere.clj:102-105
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dv, *dl, *dout;
+  float *dde;
+  Ring *drings;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(v, (size_t)count * 3, dv) || b.up(l, (size_t)count * 3, dl) ||
+      b.up(de, (size_t)shape_e[0] * shape_e[1] * 3, dde) || b.up(rings.data(), rings.size(), drings) ||
+      b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_point_scatter_batch<<<blocks((long long)count * 32, 128), 128, 0, stream()>>>(
+      P.planet, P.medium, ray_steps, src, dde, shape_e[0], shape_e[1], drings, (int)rings.size(), ndirs, count, dx, dv,
+      dl, dout);
+  CUDA_TRY(cudaGetLastError());
+  return b.down(dout, (size_t)count * 3, out);
+}
+
+extern "C" int atmlut_surface_radiance_batch(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                             int steps, const int *shape4, const float *ds_a, const float *ds_b,
+                                             int phase_component, int count, const double *x, const double *l,
+                                             double *out) {
+  Params P;
+  if (ensure_init() || make_planet_medium(planet, scatter, n, P)) return 1;
+  CHECK_ARGS(steps >= 4 && count >= 0 && shape4 && ds_a && x && l && out, "invalid argument (steps must be >= 4)");
+  CHECK_ARGS(!ds_b || (phase_component >= 0 && phase_component < n), "phase component out of range");
+  if (count == 0) return 0;
+  Bufs b;
+  TableSource src = {};
+  if (make_table_source(b, P, shape4, ds_a, ds_b, ds_b ? P.medium.g[phase_component] : 0.0, src)) return 1;
+  int ndirs = 0;
+  std::vector<Ring> rings = make_rings(steps >> 2, steps, kPi / 2, ndirs);             // sphere.clj:96-99
+  std::vector<double> cx = centred(planet, x, count);
+  double *dx, *dl, *dout;
+  Ring *drings;
+  if (b.up(cx.data(), cx.size(), dx) || b.up(l, (size_t)count * 3, dl) || b.up(rings.data(), rings.size(), drings) ||
+      b.up<double>(nullptr, (size_t)count * 3, dout))
+    return 1;
+  k_surface_radiance_batch<<<blocks((long long)count * 32, 128), 128, 0, stream()>>>(
+      P.planet, src, drings, (int)rings.size(), ndirs, count, dx, dl, dout);
   CUDA_TRY(cudaGetLastError());
   return b.down(dout, (size_t)count * 3, out);
 }

@@ -18,6 +18,10 @@
 #include "atm_device.cuh"
 #include "atm_tables.h"
 
+#ifndef ATMLUT_FO_MIN_BLOCKS
+#define ATMLUT_FO_MIN_BLOCKS 4
+#endif
+
 namespace atm {
 
 // ------------------------------------------------------------------ view ray shared by one CTA
@@ -154,6 +158,7 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
   const double inv_steps = 1.0 / (double)steps;
   const double ll = dot(l, l);
   const double llen = sqrt(ll);
+  const double inv_ll = 1.0 / ll;   // the end point of the sun ray only places samples; an ulp there is harmless
   for (int k = k0; k < k1; k++) {
     const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
     const double pl = l.x * pkx + l.y * pky;
@@ -161,10 +166,10 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
     if (!(pl >= 0 || pl * pl <= rk2 - r2)) continue;
     // atmosphere-intersection of (p_k, l) (atmosphere.clj:70-77, sphere.clj:46-59)
     const double disc = pl * pl - ll * (rk2 - rt2);
-    const double middle = -(pl / ll);
+    const double middle = -(pl * inv_ll);
     double t;
     if (disc > 0) {
-      double length2 = sqrt(disc) / ll;
+      double length2 = sqrt(disc) * inv_ll;
       t = (middle < length2) ? fmax(0.0, middle + length2) : (middle - length2) + 2 * length2;
     } else {
       t = fmax(0.0, middle);
@@ -216,7 +221,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
-__global__ void __launch_bounds__(256) k_first_order(Params P, Shard shard, int kparts, int passes, int nchunks,
+__global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
                                                      unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -775,8 +780,8 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
-  static const int warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 4)));
-  static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 2));
+  static const int warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
+  static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 1));
   const int threads = warps * 32;
   const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
   int kparts = 1, passes = 1, nchunks = 1;

@@ -296,3 +296,51 @@ def test_make_lookup_table_chain_matches_oracle():
     assert err(dE2.table, rec["dE0"]) <= 1e-4
     assert err(dS2.table, rec["dS0"]) <= 1e-4
     assert err(S, rec["S0"]) <= 1e-4
+
+
+def test_integrals_with_table_sources_at_arbitrary_points():
+    """point-scatter, surface-radiance and ray-scatter with interpolated tables as their function arguments
+    (atmosphere.clj:192-230), at points that are NOT texel centres and not in the (r, 0, 0) frame."""
+    planet = {"centre": (0, 0, 0), "radius": radius, "height": 35000.0, "brightness": (0.3, 0.3, 0.3)}
+    shape4, shape_e, steps, sphere_steps, one = (4, 9, 4, 2), (3, 7), 12, 8, (1, 1, 1)
+    pl = orc.planet(radius, 35000.0)
+    om, orr = orc.scatter(**orc.MIE), orc.scatter(**orc.RAYLEIGH)
+    cfg = orc.config(shape4, (2, 2), shape_e, steps, sphere_steps)
+    rec = {}
+    orc.generate_atmosphere_luts(pl, om, orr, cfg, iterations=1, record=rec)
+    rs_space = atm.ray_scatter_space(planet, shape4)
+    e_space = atm.surface_radiance_space(planet, shape_e)
+    r1 = itp.interpolation_table(rec["R1"], rs_space)
+    m1 = itp.interpolation_table(rec["M1"], rs_space)
+    e0 = itp.interpolation_table(rec["Ebase"], e_space)
+    dj = itp.interpolation_table(rec["dJ0"], rs_space)
+    ds_closure = itp.MieCombined(r1, m1, mie, scatter)
+    osrc = orc.SSourceSpec(r1.table.astype(np.float64), m1.table.astype(np.float64), om)
+
+    def o_lookup4(table):
+        t = table.astype(np.float64)
+        return lambda p, v, l, ab: orc.interpolate(t, orc.ray_scatter_forward(pl, shape4, p, v, l, ab))
+
+    def o_ds(p, v, l, ab):
+        return o_lookup4(r1.table)(p, v, l, ab) + o_lookup4(m1.table)(p, v, l, ab) * orc.phase(om, float(np.dot(v, l)))
+
+    def o_e(p, l):
+        return orc.interpolate(e0.table.astype(np.float64), orc.surface_radiance_forward(pl, shape_e, p, l))
+
+    x = np.array([0.3, 0.5, 0.81]) / np.linalg.norm([0.3, 0.5, 0.81]) * (radius + 4321.0)
+    l = np.array([0.48, 0.6, 0.64])
+    for v in (np.array([0.0, 0.6, 0.8]), np.array([0.6, -0.8, 0.0]), -x / np.linalg.norm(x)):
+        got = atm.point_scatter(planet, scatter, ds_closure, e0, one, sphere_steps, steps, x, v, l, True)
+        want = orc.point_scatter(pl, [om, orr], o_ds, o_e, one, sphere_steps, steps, x, v, l, True)
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+        above = orc.is_above_horizon(pl, x, v)
+        got = atm.ray_scatter(planet, scatter, steps, dj, x, v, l, above)
+        want = orc.ray_scatter(pl, [om, orr], steps, o_lookup4(dj.table), x, v, l, above)
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+    got = atm.surface_radiance(planet, ds_closure, steps, x, l)
+    want = orc.surface_radiance(pl, o_ds, steps, x, l)
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    got = atm.surface_radiance(planet, dj, steps, x, l)
+    want = orc.surface_radiance(pl, o_lookup4(dj.table), steps, x, l)
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    assert osrc is not None
