@@ -255,6 +255,15 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     stage_times = builder.stage_times()
     work = builder.work()
+    # per-rank stage times (the barrier / all-gather stages absorb the load imbalance between ranks)
+    my_stages = {}
+    for name, ms in stage_times:
+        key = name.split("_", 1)[1] if name.startswith("iter") else name
+        my_stages[key] = my_stages.get(key, 0.0) + ms
+    all_stages = [my_stages]
+    if world > 1:
+        all_stages = [None] * world
+        dist.all_gather_object(all_stages, my_stages)
 
     # end to end through the public one-shot call: host parameters in, host (pinned) tables out
     e2e = None
@@ -325,6 +334,8 @@ def run_b200(args):
                            "parallelism": ("single" if world == 1 else "%s%d" % (builder.mode, world)), "wall_s_timed_region": t_wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "stage_ms": {k: round(v, 4) for k, v in stage_dict.items()},
+                "stage_ms_max_over_ranks": {k: round(max(r[k] for r in all_stages), 4) for k in my_stages},
+                "stage_ms_min_over_ranks": {k: round(min(r[k] for r in all_stages), 4) for k in my_stages},
                 "work_per_step": work, "roofline": roofline}
         if not args.no_cpu_baseline and world == 1 and args.workload == "shipped":
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)

@@ -81,8 +81,8 @@ int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *sca
  * elevation_size, padded to per_rank pairs per rank (host-only helper, needs no device) */
 int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank);
 /* Peer-to-peer mode (alternative to the all-gather callback; one process per GPU, all on one NVSwitch box,
- * at most 8): every rank exports CUDA IPC handles of its sharded tables (6 handles of 64 bytes), the host
- * exchanges them, and every rank imports all of them in rank order (world * 6 * 64 bytes).  The kernels
+ * at most 8): every rank exports CUDA IPC handles of its sharded tables (8 handles of 64 bytes), the host
+ * exchanges them, and every rank imports all of them in rank order (world * 8 * 64 bytes).  The kernels
  * then store each finished texel into every GPU's table over NVLink, pairs are interleaved over ranks, and
  * a flag barrier replaces each all-gather. */
 int atmlut_builder_ipc_export(void *builder, unsigned char *handles, int capacity_bytes);

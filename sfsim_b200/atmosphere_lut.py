@@ -99,7 +99,7 @@ class AtmosphereLutBuilder:
 
     def _exchange_ipc_handles(self, process_group):
         import torch.distributed as dist
-        mine = C.create_string_buffer(6 * 64)
+        mine = C.create_string_buffer(8 * 64)
         check(self.lib.atmlut_builder_ipc_export(self.handle, mine, len(mine)))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, bytes(mine.raw), group=process_group)

@@ -152,7 +152,8 @@ struct Builder {
   // peer-to-peer mode: every sharded table also mapped on the peers (CUDA IPC), flag words for the barrier
   bool p2p = false;
   int he_stride = 1;
-  PeerOut peer_R1 = {}, peer_M1 = {}, peer_dJ = {}, peer_dS = {}, peer_dS2 = {};
+  PeerOut peer_R1 = {}, peer_M1 = {}, peer_dJ = {}, peer_dS = {}, peer_dS2 = {}, peer_S = {}, peer_S_new = {};
+  unsigned epoch_side = 0;
   unsigned *flags = nullptr;
   int *error_flag = nullptr;
   unsigned *peer_flags[kMaxPeers] = {};
@@ -235,14 +236,16 @@ static int builder_alloc(Builder &b) {
   if (dev_alloc(b.file_S, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.file_M, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.counter, 2)) return 1;
-  if (dev_alloc(b.flags, kMaxPeers) || dev_alloc(b.error_flag, 1)) return 1;
-  CUDA_TRY(cudaMemsetAsync(b.flags, 0, kMaxPeers * sizeof(unsigned), g_stream));
+  if (dev_alloc(b.flags, 2 * kMaxPeers) || dev_alloc(b.error_flag, 1)) return 1;
+  CUDA_TRY(cudaMemsetAsync(b.flags, 0, 2 * kMaxPeers * sizeof(unsigned), g_stream));
   CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), g_stream));
   b.peer_R1 = local_out(b.R1);
   b.peer_M1 = local_out(b.M1);
   b.peer_dJ = local_out(b.dJ);
   b.peer_dS = local_out(b.dS);
   b.peer_dS2 = local_out(b.dS2);
+  b.peer_S = local_out(b.S);
+  b.peer_S_new = local_out(b.S_new);
   std::vector<double> dirs, w;
   sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);  // sphere.clj:102-105
   b.n_sphere = (int)w.size();
@@ -279,8 +282,27 @@ static int stage_end(Builder &b) {
 
 static int peer_barrier(Builder &b) {
   b.epoch++;
-  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, b.rank, b.world, b.epoch, b.error_flag, g_stream));
+  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 0, b.rank, b.world, b.epoch, b.error_flag, g_stream));
   b.launches++;
+  return 0;
+}
+
+// S += dS (atmosphere_lut.clj:96-97).  Peer-to-peer mode shards it like the integration kernels: every rank
+// re-tabulates its own pairs into all GPUs' copies and a side-stream barrier closes the table.  Otherwise
+// every rank re-tabulates the whole table (cheaper than a collective for this small kernel).
+static int accumulate_s(Builder &b, const float4 *s_cur, const float4 *ds) {
+  const Params &P = b.P;
+  if (b.p2p && b.world > 1) {
+    CUDA_TRY(launch_resample_4d(P, Shard{b.he_begin, b.he_stride}, b.he_count, s_cur, ds, b.peer_S_new, nullptr, b.side));
+    b.epoch_side++;
+    CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 1, b.rank, b.world, b.epoch_side, b.error_flag, b.side));
+    b.launches += 2;
+  } else {
+    CUDA_TRY(launch_resample_4d(P, Shard{0, 1}, b.n_he, s_cur, ds, local_out(b.S_new), nullptr, b.side));
+    b.launches++;
+  }
+  std::swap(b.S, b.S_new);
+  std::swap(b.peer_S, b.peer_S_new);
   return 0;
 }
 
@@ -397,10 +419,9 @@ static int builder_run(Builder &b) {
     std::swap(b.Eacc, b.Eacc_new);
     e_cur = b.Eacc;
     if (it == 0) {
-      LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, side)); // :101,105
+      LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, b.M1, nullptr, local_out(nullptr), b.file_M, side)); // :101,105
     } else {
-      LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, ds.tab_a, b.S_new, nullptr, side));  // :96-97
-      std::swap(b.S, b.S_new);
+      TRY(accumulate_s(b, s_cur, ds.tab_a));                                          // :96-97
       s_cur = b.S;
     }
     TRY(event_at(b, ev++, side_done[it]));
@@ -445,14 +466,13 @@ static int builder_run(Builder &b) {
     CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
     CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), side));       // :76 E = 0
     e_cur = b.Eacc;
-    LAUNCH(launch_resample_4d(P, 0, b.n4, b.M1, nullptr, nullptr, b.file_M, side));   // :101,105
+    LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, b.M1, nullptr, local_out(nullptr), b.file_M, side));   // :101,105
   } else {
-    LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, ds.tab_a, b.S_new, nullptr, side));  // :96-97 (last order)
-    std::swap(b.S, b.S_new);
+    TRY(accumulate_s(b, s_cur, ds.tab_a));                                            // :96-97 (last order)
     s_cur = b.S;
   }
   LAUNCH(launch_resample_2d(P, 1, e_cur, nullptr, nullptr, b.file_E, side));          // :99,103
-  LAUNCH(launch_resample_4d(P, 0, b.n4, s_cur, nullptr, nullptr, b.file_S, side));    // :100,104
+  LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, s_cur, nullptr, local_out(nullptr), b.file_S, side));    // :100,104
   TRY(order_after(b, ev, side, st));
   TRY(stage_end(b));
   b.ran = true;
@@ -559,13 +579,13 @@ extern "C" int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *co
 }
 
 // ---- peer-to-peer mode: CUDA IPC handles of the sharded tables and the barrier flags ----
-static const int kIpcTables = 6;   // R1, M1, dJ, dS, dS2, flags
+static const int kIpcTables = 8;   // R1, M1, dJ, dS, dS2, S, S_new, flags
 
 extern "C" int atmlut_builder_ipc_export(void *builder, unsigned char *handles, int capacity_bytes) {
   Builder *b = (Builder *)builder;
   if (!b || !handles) return fail("invalid argument");
   if (capacity_bytes < kIpcTables * (int)sizeof(cudaIpcMemHandle_t)) return fail("handle buffer too small");
-  void *ptrs[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->flags};
+  void *ptrs[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->S, b->S_new, b->flags};
   for (int i = 0; i < kIpcTables; i++) {
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, ptrs[i]));
@@ -580,11 +600,12 @@ extern "C" int atmlut_builder_ipc_import(void *builder, const unsigned char *all
   if (world != b->world) return fail("world size mismatch");
   if (world > kMaxPeers) return fail("peer-to-peer mode supports at most 8 GPUs");
   if (b->p2p) return fail("peer handles were already imported");
-  PeerOut *outs[5] = {&b->peer_R1, &b->peer_M1, &b->peer_dJ, &b->peer_dS, &b->peer_dS2};
+  if (b->ran) return fail("import the peer handles before the first run");
+  PeerOut *outs[7] = {&b->peer_R1, &b->peer_M1, &b->peer_dJ, &b->peer_dS, &b->peer_dS2, &b->peer_S, &b->peer_S_new};
   for (int q = 0; q < world; q++) {
     void *ptrs[kIpcTables];
     if (q == b->rank) {
-      void *mine[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->flags};
+      void *mine[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->S, b->S_new, b->flags};
       memcpy(ptrs, mine, sizeof mine);
     } else {
       for (int i = 0; i < kIpcTables; i++) {
@@ -593,9 +614,9 @@ extern "C" int atmlut_builder_ipc_import(void *builder, const unsigned char *all
         CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
         b->ipc_opened.push_back(ptrs[i]);
       }
-      for (int i = 0; i < 5; i++) outs[i]->p[outs[i]->n++] = (float4 *)ptrs[i];
+      for (int i = 0; i < 7; i++) outs[i]->p[outs[i]->n++] = (float4 *)ptrs[i];
     }
-    b->peer_flags[q] = (unsigned *)ptrs[5];
+    b->peer_flags[q] = (unsigned *)ptrs[7];
   }
   // interleaved pairs: rank r integrates pairs r, r + world, ... (balances cost; no layout constraint here)
   b->p2p = true;
@@ -935,7 +956,7 @@ extern "C" int atmlut_resample_table(const atmlut_planet *planet, const atmlut_c
   float4 *da = nullptr, *db = nullptr, *o = nullptr;
   if ((a && d.upload_rgb(a, n, da)) || (b && d.upload_rgb(b, n, db)) || d.alloc(o, (size_t)n)) return 1;
   if (which == 0)
-    CUDA_TRY(launch_resample_4d(P, 0, n, da, db, o, nullptr, g_stream));
+    CUDA_TRY(launch_resample_4d(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], da, db, local_out(o), nullptr, g_stream));
   else
     CUDA_TRY(launch_resample_2d(P, which, da, db, o, nullptr, g_stream));
   return d.download_rgb(o, n, out);

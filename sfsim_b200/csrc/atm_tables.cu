@@ -644,11 +644,14 @@ __global__ void __launch_bounds__(256) k_surface_radiance(Params P, SSource src,
 
 // out[i] = lookup(a, g(i)) [+ lookup(b, g(i))], g = ray-scatter-forward o ray-scatter-backward.
 // file_layout != 0: write packed RGB float in convert-4d-to-2d order (image.clj:299-312).
-__global__ void k_resample_4d(Params P, long long begin, long long count, const float4 *__restrict__ a,
-                              const float4 *__restrict__ b, float4 *out, float *file_out) {
-  long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= begin + count) return;
+__global__ void k_resample_4d(Params P, Shard shard, long long count, const float4 *__restrict__ a,
+                              const float4 *__restrict__ b, PeerOut out, float *file_out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // j-th texel of this launch
+  if (j >= count) return;
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  // texels are taken pair by pair: pair shard.begin + n * shard.stride, all of its S*A texels
+  const int ntex = S * A;
+  const long long i = ((long long)shard.begin + (j / ntex) * shard.stride) * ntex + j % ntex;
   const int ai = (int)(i % A), si = (int)((i / A) % S), ei = (int)((i / ((long long)A * S)) % E),
             hi = (int)(i / ((long long)A * S * E));
   V3 x, v, l;
@@ -665,7 +668,7 @@ __global__ void k_resample_4d(Params P, long long begin, long long count, const 
     r.y += t.y;
     r.z += t.z;
   }
-  if (out) out[i] = r;
+  store_all(out, (size_t)i, r);
   if (file_out) {
     const long long y = (long long)hi * S + si, xx = (long long)ei * A + ai;
     float *o = file_out + (y * ((long long)E * A) + xx) * 3;
@@ -735,12 +738,13 @@ struct PeerFlags {
 // GPU.  The kernels whose stores must be visible ran earlier on the same stream; the system-scope fence
 // orders them before the flag.  Epochs only grow, so a GPU that runs ahead never confuses a slower one.
 // A peer that never arrives (crashed process) trips the clock-based timeout instead of hanging the box.
-__global__ void k_peer_barrier(unsigned *local_flags, PeerFlags peers, int rank, int world, unsigned epoch,
+__global__ void k_peer_barrier(unsigned *local_flags, PeerFlags peers, int offset, int rank, int world, unsigned epoch,
                                int *error_flag) {
   const int q = threadIdx.x;
   if (q >= world) return;
+  local_flags += offset;   // independent flag sets for the two streams
   __threadfence_system();
-  volatile unsigned *remote = peers.p[q] + rank;
+  volatile unsigned *remote = peers.p[q] + offset + rank;
   *remote = epoch;
   __threadfence_system();
   volatile unsigned *mine = local_flags + q;
@@ -860,10 +864,11 @@ cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *
   return cudaGetLastError();
 }
 
-cudaError_t launch_resample_4d(const Params &P, long long begin, long long count, const float4 *a, const float4 *b,
-                               float4 *out, float *file_out, cudaStream_t st) {
+cudaError_t launch_resample_4d(const Params &P, Shard shard, int pair_count, const float4 *a, const float4 *b,
+                               PeerOut out, float *file_out, cudaStream_t st) {
+  const long long count = (long long)pair_count * P.shapes.s4[2] * P.shapes.s4[3];
   if (count <= 0) return cudaSuccess;
-  k_resample_4d<<<div_up(count, 128), 128, 0, st>>>(P, begin, count, a, b, out, file_out);
+  k_resample_4d<<<div_up(count, 128), 128, 0, st>>>(P, shard, count, a, b, out, file_out);
   return cudaGetLastError();
 }
 
@@ -875,11 +880,11 @@ cudaError_t launch_resample_2d(const Params &P, int which, const float4 *a, cons
   return cudaGetLastError();
 }
 
-cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int rank, int world,
+cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int flag_set, int rank, int world,
                                 unsigned epoch, int *error_flag, cudaStream_t st) {
   PeerFlags f = {};
   for (int q = 0; q < world && q < kMaxPeers; q++) f.p[q] = peer_flags[q];
-  k_peer_barrier<<<1, 32, 0, st>>>(local_flags, f, rank, world, epoch, error_flag);
+  k_peer_barrier<<<1, 32, 0, st>>>(local_flags, f, flag_set * kMaxPeers, rank, world, epoch, error_flag);
   return cudaGetLastError();
 }
 

@@ -73,7 +73,8 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
 cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, PeerOut out,
                                unsigned long long *counter, cudaStream_t st);
 // cross-GPU barrier over peer-mapped flag words: signal `epoch` to every peer, wait for every peer's signal
-cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int rank, int world,
+// flag_set 0 / 1: independent barriers for the main and the side stream (kMaxPeers words each)
+cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int flag_set, int rank, int world,
                                 unsigned epoch, int *error_flag, cudaStream_t st);
 cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
                                          cudaStream_t st);
@@ -90,8 +91,9 @@ cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs,
                                             cudaStream_t st);
 cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *dirs, const double *weights,
                                     int ndirs, const HalfDirInfo *info, float4 *out, cudaStream_t st);
-cudaError_t launch_resample_4d(const Params &P, long long begin, long long count, const float4 *a, const float4 *b,
-                               float4 *out, float *file_out, cudaStream_t st);
+// re-tabulates the pairs shard.begin + n * shard.stride, n < pair_count
+cudaError_t launch_resample_4d(const Params &P, Shard shard, int pair_count, const float4 *a, const float4 *b,
+                               PeerOut out, float *file_out, cudaStream_t st);
 cudaError_t launch_resample_2d(const Params &P, int which, const float4 *a, const float4 *b, float4 *out,
                                float *file_out, cudaStream_t st);
 cudaError_t launch_rgb_to_float4(const float *in, float4 *out, long long n, cudaStream_t st);
