@@ -35,6 +35,22 @@ int ensure_init() {
 
 cudaStream_t stream() { return g_stream; }
 
+// exp(i/64), i = -256 .. 0, for the kernels' exp_tab (host libm values)
+static double *g_exp_table = nullptr;
+
+int exp_table(const double *&table) {
+  if (!g_exp_table) {
+    std::vector<double> host(kExpTabSize);
+    for (int i = 0; i < kExpTabSize; i++) host[i] = exp((double)(i - (kExpTabSize - 1)) / 64.0);
+    cudaError_t e = cudaMalloc((void **)&g_exp_table, kExpTabSize * sizeof(double));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exp table)");
+    e = cudaMemcpy(g_exp_table, host.data(), kExpTabSize * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(exp table)");
+  }
+  table = g_exp_table;
+  return 0;
+}
+
 // ------------------------------------------------------------------ parameters
 
 int make_planet_medium(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, Params &P) {
@@ -369,6 +385,8 @@ static int builder_run(Builder &b) {
   const PeerOut dsout[2] = {b.peer_dS, b.peer_dS2};
   float4 *debuf[2] = {b.dE, b.dE_new};
   const int N = b.iterations;
+  const double *etab = nullptr;
+  TRY(exp_table(etab));
 
   CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
   // peer-to-peer mode: nobody may store into a peer's tables before that peer has finished its previous run
@@ -436,7 +454,7 @@ static int builder_run(Builder &b) {
       if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_b, st));
     }
     LAUNCH(launch_point_scatter(P, shard, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
-                                debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, b.peer_dJ, st));  // :88,90
+                                debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, etab, b.peer_dJ, st));  // :88,90
     // the next ray-scatter overwrites the buffer of dS_{it-1} (on every GPU in peer-to-peer mode): this
     // rank's side stream must be done reading it before the barrier / all-gather below lets anyone go on
     if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
@@ -450,7 +468,7 @@ static int builder_run(Builder &b) {
     snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
     TRY(stage_begin(b, name));
     float4 *ds_next = dsbuf[(it + 1) & 1];
-    LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.dJ, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
+    LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.dJ, etab, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_ray_scatter_allgather", it + 1);
     TRY(stage_begin(b, name));
@@ -516,6 +534,8 @@ extern "C" void *atmlut_stream(void) { return (void *)g_stream; }
 
 extern "C" void atmlut_destroy(void) {
   drop_generate_cache();
+  if (g_exp_table) cudaFree(g_exp_table);
+  g_exp_table = nullptr;
   if (g_stream) {
     cudaStreamSynchronize(g_stream);
     cudaStreamDestroy(g_stream);
@@ -892,13 +912,15 @@ extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atm
   if (d.upload_doubles(dirs, ddirs) || d.upload_doubles(w, dw) || d.alloc(info, (size_t)P.shapes.s4[0] * w.size()))
     return 1;
   CUDA_TRY(launch_point_scatter_prepare(P, ddirs, (int)w.size(), info, g_stream));
+  const double *etab = nullptr;
+  if (exp_table(etab)) return 1;
   float4 *ta = nullptr, *tb = nullptr;
   const size_t tile_count = (size_t)P.shapes.s4[0] * w.size() * P.shapes.s4[2] * P.shapes.s4[3];
   if (d.alloc(ta, tile_count) || (b && d.alloc(tb, tile_count))) return 1;
   CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), 0, P.shapes.s4[0], ta, g_stream));
   if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), 0, P.shapes.s4[0], tb, g_stream));
   CUDA_TRY(launch_point_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
-                                ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info,
+                                ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info, etab,
                                 local_out(o), g_stream));
   return d.download_rgb(o, n4, out);
 }
@@ -939,7 +961,9 @@ extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlu
   const long long n4 = n4_of(P);
   float4 *j = nullptr, *o = nullptr;
   if (d.upload_rgb(dj, n4, j) || d.alloc(o, (size_t)n4)) return 1;
-  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, local_out(o), nullptr, g_stream));
+  const double *etab = nullptr;
+  if (exp_table(etab)) return 1;
+  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, etab, local_out(o), nullptr, g_stream));
   return d.download_rgb(o, n4, out);
 }
 

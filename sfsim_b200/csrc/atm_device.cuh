@@ -199,6 +199,39 @@ __device__ __forceinline__ void transmittance_rgb(const Fast &f, float c0, float
   }
 }
 
+// ------------------------------------------------------------------ sun-elevation lookup coordinate
+
+// exp(y) for y in [-4, 0] to double accuracy from a table of exp(i/64) (in shared memory, filled with the
+// host's exp) and a degree-4 polynomial on the remainder |y - i/64| <= 1/128 (truncation 2.4e-13 relative).
+// The library exp costs ~60 issue slots here (11 polynomial constants reloaded through the uniform datapath);
+// this one costs 12.  Used only for lookup coordinates, which are continuous in it.
+constexpr int kExpTabSize = 4 * 64 + 1;   // i = -256 .. 0
+
+__device__ __forceinline__ double exp_tab(const double *tab, double y) {
+  const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of y*64 + magic is rint(y*64)
+  const double t = fma(y, 64.0, magic);
+  const int i = __double2loint(t);                    // -256 .. 0
+  const double r = fma(t - magic, -1.0 / 64.0, y);    // y - i/64
+  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return tab[i + (kExpTabSize - 1)] * p;
+}
+
+__device__ __forceinline__ void fill_exp_tab(double *tab, const double *global_tab) {
+  for (int i = threadIdx.x; i < kExpTabSize; i += blockDim.x) tab[i] = global_tab[i];
+}
+
+// atmosphere.clj:322-326 for lookups inside the integration kernels, from the sine of the sun elevation.
+// sin <= -0.2 is below the table's range: the reference's max(0, .) gives exactly 0 there.
+__device__ __forceinline__ double sun_elevation_coord(const double *exp_table, int size, double sin_elevation) {
+  const double inv = 1.0 / (1 - 0.02732372244729256);   // 1 / (1 - exp(-3.6))
+  const double y = fmax(0 - 3 * sin_elevation - 0.6, -4.0);
+  if (y >= 0.0) return 0.0;
+  return (double)(size - 1) * fmax(0.0, (1 - exp_tab(exp_table, y)) * inv);
+}
+
 // ------------------------------------------------------------------ float4 table lookups
 
 // interpolate.clj:75-98: clip to [0, n-1], u = floor, v = min(u + 1, n - 1), s = i - u

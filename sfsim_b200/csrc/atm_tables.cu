@@ -299,6 +299,7 @@ struct alignas(16) LookupSmem {
   float tr[kMaxSteps][3];      // T(x -> p_k)
   double rk[kMaxSteps];        // |p_k|
   double nx[kMaxSteps], ny[kMaxSteps];   // p_k / |p_k|
+  double exp_table[kExpTabSize + 3];     // exp(i/64), i = -256 .. 0 (exp_tab)
 };
 
 // dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with
@@ -310,7 +311,8 @@ struct alignas(16) LookupSmem {
 // loads, double buffered), and each texel then interpolates inside that tile: 4 shared-memory loads
 // per lookup instead of 16 scattered global ones.
 __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, const float4 *__restrict__ dj,
-                                                      PeerOut out, unsigned long long *counter) {
+                                                      const double *__restrict__ exp_table, PeerOut out,
+                                                      unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
   LookupSmem &ls = *reinterpret_cast<LookupSmem *>(smem_raw + sizeof(ViewSmem));
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
+  fill_exp_tab(ls.exp_table, exp_table);
   setup_view_ray(P, h, e, vs, esamples);
   const ViewRay ray = vs.ray;
   const V3 v = v3(ray.vx, ray.vy, 0.0);
@@ -355,16 +358,40 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
     const Axis aa = axis_from(sun_angle_to_index(A, v, l), A);
     float acc[3] = {0.f, 0.f, 0.f};
+    // When the tile has at most one element per thread its four corner loads for sample k + 1 are issued
+    // before the lookups of sample k (software pipelining: the L2 latency hides behind the FP64 coordinate
+    // math instead of being exposed in front of every barrier).
+    const bool one_per_thread = ntex <= (int)blockDim.x;
+    const bool loader = (int)threadIdx.x < ntex;
+    float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+    if (one_per_thread && loader) {
+      const int4 rows = *reinterpret_cast<const int4 *>(ls.row[0]);
+      c00 = ldg4(dj + rows.x + threadIdx.x);
+      c01 = ldg4(dj + rows.y + threadIdx.x);
+      c10 = ldg4(dj + rows.z + threadIdx.x);
+      c11 = ldg4(dj + rows.w + threadIdx.x);
+    }
     for (int k = 0; k < steps; k++) {
       float4 *tile = tiles + (size_t)(k & 1) * ntex;
       {
-        const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k]);
-        const float4 *t00 = dj + rows.x, *t01 = dj + rows.y, *t10 = dj + rows.z, *t11 = dj + rows.w;
         const float es = ls.es[k], hs = ls.hs[k];
-        for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
-          tile[idx] = mix4(mix4(ldg4(t00 + idx), ldg4(t01 + idx), es), mix4(ldg4(t10 + idx), ldg4(t11 + idx), es), hs);
+        if (one_per_thread) {
+          if (loader) tile[threadIdx.x] = mix4(mix4(c00, c01, es), mix4(c10, c11, es), hs);
+        } else {
+          const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k]);
+          const float4 *t00 = dj + rows.x, *t01 = dj + rows.y, *t10 = dj + rows.z, *t11 = dj + rows.w;
+          for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
+            tile[idx] = mix4(mix4(ldg4(t00 + idx), ldg4(t01 + idx), es), mix4(ldg4(t10 + idx), ldg4(t11 + idx), es), hs);
+        }
       }
       __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
+      if (one_per_thread && loader && k + 1 < steps) {
+        const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k + 1]);
+        c00 = ldg4(dj + rows.x + threadIdx.x);
+        c01 = ldg4(dj + rows.y + threadIdx.x);
+        c10 = ldg4(dj + rows.z + threadIdx.x);
+        c11 = ldg4(dj + rows.w + threadIdx.x);
+      }
       if (active) {
         // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
         // float32 coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         // that rows the reference clamps to exactly 0 are clamped here as well.
         double sin_elev = l.x * ls.nx[k] + l.y * ls.ny[k];
         if (sin_elev < -0.2 + 1e-9) sin_elev = (l.x * vs.pkx[k] + l.y * vs.pky[k]) / ls.rk[k];
-        const Axis as = axis_from(sin_sun_elevation_to_index_fast(S, sin_elev), S);
+        const Axis as = axis_from(sun_elevation_coord(ls.exp_table, S, sin_elev), S);
         const float4 j = lookup2_smem(tile, A, as, aa);
         acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
         acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
@@ -466,10 +493,13 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
                                                        const float4 *__restrict__ de,
                                                        const double *__restrict__ dirs,
                                                        const double *__restrict__ weights, int ndirs,
-                                                       const DirInfo *__restrict__ info, PeerOut out) {
+                                                       const DirInfo *__restrict__ info,
+                                                       const double *__restrict__ exp_table, PeerOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PointDir *pd = reinterpret_cast<PointDir *>(smem_raw);
   __shared__ double s_geom[4];
+  __shared__ double s_exp[kExpTabSize];
+  fill_exp_tab(s_exp, exp_table);
   const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int he = shard.begin + blockIdx.x * shard.stride;
   const int h = he / E, e = he % E;
@@ -553,7 +583,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
         // lower clamp it is recomputed as the reference writes it, (dot point l) / (mag point)
         double sin_elev = r.ux * l.x + r.uy * l.y + r.uz * l.z;
         if (sin_elev < -0.2 + 1e-9) sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
-        Axis es = axis_from(sin_sun_elevation_to_index_fast(P.shapes.se[1], sin_elev), P.shapes.se[1]);
+        Axis es = axis_from(sun_elevation_coord(s_exp, P.shapes.se[1], sin_elev), P.shapes.se[1]);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
         s.x = fmaf(r.tb[0], ev.x, s.x);
         s.y = fmaf(r.tb[1], ev.y, s.y);
@@ -812,14 +842,14 @@ size_t ray_scatter_smem(const Params &P) {
   return sizeof(ViewSmem) + sizeof(LookupSmem) + 2 * (size_t)P.shapes.s4[2] * P.shapes.s4[3] * sizeof(float4);
 }
 
-cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, PeerOut out,
-                               unsigned long long *counter, cudaStream_t st) {
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, const double *exp_table,
+                               PeerOut out, unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   size_t smem = ray_scatter_smem(P);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // light-elevation x heading tile too large
   cudaError_t e = cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, out, counter);
+  k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, exp_table, out, counter);
   return cudaGetLastError();
 }
 
@@ -839,14 +869,14 @@ cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const Dir
 
 cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
-                                 const double *weights, int ndirs, const DirInfo *info, PeerOut out,
-                                 cudaStream_t st) {
+                                 const double *weights, int ndirs, const DirInfo *info, const double *exp_table,
+                                 PeerOut out, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   size_t smem = (size_t)ndirs * sizeof(PointDir);
   cudaError_t e = cudaFuncSetAttribute(k_point_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_point_scatter<<<he_count, 256, smem, st>>>(P, shard, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info,
-                                               out);
+                                               exp_table, out);
   return cudaGetLastError();
 }
 

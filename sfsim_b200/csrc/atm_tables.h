@@ -70,8 +70,9 @@ cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_
 cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st);
 cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
                                unsigned long long *counter, cudaStream_t st);
-cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, PeerOut out,
-                               unsigned long long *counter, cudaStream_t st);
+// exp_table: device array of kExpTabSize doubles, exp(i/64) for i = -256 .. 0 (see exp_tab)
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, const double *exp_table,
+                               PeerOut out, unsigned long long *counter, cudaStream_t st);
 // cross-GPU barrier over peer-mapped flag words: signal `epoch` to every peer, wait for every peer's signal
 // flag_set 0 / 1: independent barriers for the main and the side stream (kMaxPeers words each)
 cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int flag_set, int rank, int world,
@@ -84,8 +85,8 @@ cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const Dir
 // tiles_a / tiles_b: blended [height][direction][light-elevation][heading] tiles of the S source
 cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
-                                 const double *weights, int ndirs, const DirInfo *info, PeerOut out,
-                                 cudaStream_t st);
+                                 const double *weights, int ndirs, const DirInfo *info, const double *exp_table,
+                                 PeerOut out, cudaStream_t st);
 size_t ray_scatter_smem(const Params &P);
 cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,
                                             cudaStream_t st);
