@@ -69,6 +69,12 @@ void atmlut_default_config(atmlut_config *cfg); /* shipped constants, atmosphere
 int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, const atmlut_config *cfg,
                     float *transmittance, float *surface_radiance, float *ray_scatter, float *mie_strength);
 
+/* The same call spread over the first `num_gpus` GPUs of the box (<= 8, peer access required) from ONE host
+ * process and thread -- the form the Clojure host uses.  Results are byte-identical to atmlut_generate. */
+int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, const atmlut_config *cfg,
+                          int num_gpus, float *transmittance, float *surface_radiance, float *ray_scatter,
+                          float *mie_strength);
+
 /* ---- device-resident builder: same computation, split so a host can shard it over GPUs ----
  * Rank r of `world` computes a contiguous slab of every 4-D table; after each table the
  * `allgather` callback (if set) must make buf[0 .. world*bytes_per_rank) identical on all ranks,

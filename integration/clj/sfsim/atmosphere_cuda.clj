@@ -61,10 +61,13 @@
 (defcfn atmlut-destroy "Release the library's device resources" atmlut_destroy [] ::mem/void)
 (defcfn atmlut-last-error "Message of the last failed call" atmlut_last_error [] ::mem/c-string)
 
+(defcfn atmlut-device-count "Number of CUDA devices" atmlut_device_count [] ::mem/int)
+
 (defcfn atmlut-generate-
-  "generate-atmosphere-luts on the GPU (private)"
-  atmlut_generate
-  [::mem/pointer ::mem/pointer ::mem/int ::mem/pointer ::mem/pointer ::mem/pointer ::mem/pointer ::mem/pointer]
+  "generate-atmosphere-luts on the first num-gpus GPUs of the box, driven from this one JVM thread (private)"
+  atmlut_generate_multi
+  [::mem/pointer ::mem/pointer ::mem/int ::mem/pointer ::mem/int
+   ::mem/pointer ::mem/pointer ::mem/pointer ::mem/pointer]
   ::mem/int)
 
 
@@ -76,7 +79,7 @@
 
 
 (defn generate-tables
-  "Compute the four tables; returns float arrays in file layout
+  "Compute the four tables on all GPUs of the box (at most 8); returns float arrays in file layout
    [transmittance surface-radiance ray-scatter mie-strength]"
   [planet scatter {:keys [height-size elevation-size light-elevation-size heading-size
                           transmittance-height-size transmittance-elevation-size
@@ -94,7 +97,7 @@
           e*      (mem/alloc (* 4 n-e) arena)
           s*      (mem/alloc (* 4 n-s) arena)
           m*      (mem/alloc (* 4 n-s) arena)]
-      (check (atmlut-generate- planet* scatter* (count scatter) config* t* e* s* m*))
+      (check (atmlut-generate- planet* scatter* (count scatter) config* (min 8 (atmlut-device-count)) t* e* s* m*))
       (mapv (fn [segment n] (float-array (mem/deserialize-from segment [::mem/array ::mem/float n])))
             [t* e* s* m*] [n-t n-e n-s n-s]))))
 

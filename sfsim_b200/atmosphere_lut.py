@@ -37,15 +37,20 @@ def allocate_outputs(cfg, pinned=False):
     return [np.empty(s, dtype=np.float32) for s in shapes]
 
 
-def generate_tables(planet=earth, scatter=(mie, rayleigh), cfg=None, out=None):
+def generate_tables(planet=earth, scatter=(mie, rayleigh), cfg=None, out=None, num_gpus=1):
     """generate-atmosphere-luts up to (not including) the file writes; returns the four float32 arrays
-    in file layout.  One call into the library: atmlut_generate."""
+    in file layout.  One call into the library: atmlut_generate, or atmlut_generate_multi when the build
+    is to be spread over `num_gpus` GPUs from this one process."""
     lib = _lib.load()
     cfg = cfg or _lib.default_config()
     out = out or allocate_outputs(cfg)
     pl = _lib.make_planet(planet)
     sc = _lib.make_scatter_array(scatter)
-    check(lib.atmlut_generate(C.byref(pl), sc, len(scatter), C.byref(cfg), *[_lib.ptr(o) for o in out]))
+    if num_gpus == 1:
+        check(lib.atmlut_generate(C.byref(pl), sc, len(scatter), C.byref(cfg), *[_lib.ptr(o) for o in out]))
+    else:
+        check(lib.atmlut_generate_multi(C.byref(pl), sc, len(scatter), C.byref(cfg), int(num_gpus),
+                                        *[_lib.ptr(o) for o in out]))
     return out
 
 
@@ -62,9 +67,9 @@ def write_tables(tables, out_dir):
     return paths
 
 
-def generate_atmosphere_luts(out_dir="data/atmosphere", planet=earth, scatter=(mie, rayleigh), cfg=None):
+def generate_atmosphere_luts(out_dir="data/atmosphere", planet=earth, scatter=(mie, rayleigh), cfg=None, num_gpus=1):
     """Program to generate lookup tables for atmospheric scattering (atmosphere_lut.clj:43-105)."""
-    return write_tables(generate_tables(planet, scatter, cfg), out_dir)
+    return write_tables(generate_tables(planet, scatter, cfg, num_gpus=num_gpus), out_dir)
 
 
 class AtmosphereLutBuilder:

@@ -35,19 +35,22 @@ int ensure_init() {
 
 cudaStream_t stream() { return g_stream; }
 
-// exp(i/64), i = -256 .. 0, for the kernels' exp_tab (host libm values)
-static double *g_exp_table = nullptr;
+// exp(i/64), i = -256 .. 0, for the kernels' exp_tab (host libm values), one copy per device
+static double *g_exp_table[64] = {};
 
 int exp_table(const double *&table) {
-  if (!g_exp_table) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail("cannot identify the current device");
+  if (!g_exp_table[dev]) {
     std::vector<double> host(kExpTabSize);
     for (int i = 0; i < kExpTabSize; i++) host[i] = exp((double)(i - (kExpTabSize - 1)) / 64.0);
-    cudaError_t e = cudaMalloc((void **)&g_exp_table, kExpTabSize * sizeof(double));
+    e = cudaMalloc((void **)&g_exp_table[dev], kExpTabSize * sizeof(double));
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exp table)");
-    e = cudaMemcpy(g_exp_table, host.data(), kExpTabSize * sizeof(double), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(g_exp_table[dev], host.data(), kExpTabSize * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(exp table)");
   }
-  table = g_exp_table;
+  table = g_exp_table[dev];
   return 0;
 }
 
@@ -164,6 +167,9 @@ struct Builder {
   // device tables (float4)
   float4 *T = nullptr, *dE = nullptr, *dE_new = nullptr, *Eacc = nullptr, *Eacc_new = nullptr;
   float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dS2 = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
+  int device = 0;                          // CUDA device of this builder
+  cudaStream_t main = nullptr;             // main stream (the library stream, or its own in a multi-GPU group)
+  bool own_main = false;
   cudaStream_t side = nullptr;             // second stream of the build DAG
   // peer-to-peer mode: every sharded table also mapped on the peers (CUDA IPC), flag words for the barrier
   bool p2p = false;
@@ -190,6 +196,7 @@ struct Builder {
   long long launches = 0;   // kernels launched by the last run
 
   ~Builder() {
+    cudaSetDevice(device);
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dS2, dJ, S, S_new, file_T, file_E, file_S, file_M,
                     sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
                     tiles_a, tiles_b};
@@ -204,6 +211,7 @@ struct Builder {
     if (flags) cudaFree(flags);
     if (error_flag) cudaFree(error_flag);
     if (side) cudaStreamDestroy(side);
+    if (own_main && main) cudaStreamDestroy(main);
   }
 };
 
@@ -213,10 +221,10 @@ static int dev_alloc(T *&p, size_t count) {
   return 0;
 }
 
-static int upload(double *&dst, const std::vector<double> &src) {
+static int upload(double *&dst, const std::vector<double> &src, cudaStream_t stream) {
   if (dev_alloc(dst, src.size())) return 1;
-  CUDA_TRY(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  CUDA_TRY(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
   return 0;
 }
 
@@ -241,7 +249,7 @@ static int builder_alloc(Builder &b) {
   float4 **four[] = {&b.R1, &b.M1, &b.dS, &b.dS2, &b.dJ, &b.S, &b.S_new};
   for (auto p : four) {
     if (dev_alloc(*p, (size_t)b.n4_pad)) return 1;
-    CUDA_TRY(cudaMemsetAsync(*p, 0, (size_t)b.n4_pad * sizeof(float4), g_stream));
+    CUDA_TRY(cudaMemsetAsync(*p, 0, (size_t)b.n4_pad * sizeof(float4), b.main));
   }
   float4 **two[] = {&b.dE, &b.dE_new, &b.Eacc, &b.Eacc_new};
   for (auto p : two)
@@ -253,8 +261,8 @@ static int builder_alloc(Builder &b) {
   if (dev_alloc(b.file_M, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.counter, 2)) return 1;
   if (dev_alloc(b.flags, 2 * kMaxPeers) || dev_alloc(b.error_flag, 1)) return 1;
-  CUDA_TRY(cudaMemsetAsync(b.flags, 0, 2 * kMaxPeers * sizeof(unsigned), g_stream));
-  CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), g_stream));
+  CUDA_TRY(cudaMemsetAsync(b.flags, 0, 2 * kMaxPeers * sizeof(unsigned), b.main));
+  CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), b.main));
   b.peer_R1 = local_out(b.R1);
   b.peer_M1 = local_out(b.M1);
   b.peer_dJ = local_out(b.dJ);
@@ -266,11 +274,11 @@ static int builder_alloc(Builder &b) {
   sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);  // sphere.clj:102-105
   b.n_sphere = (int)w.size();
   if (b.n_sphere > kMaxDirs) return fail("sphere_steps too large for the point-scatter kernel");
-  if (upload(b.sphere_dirs, dirs) || upload(b.sphere_w, w)) return 1;
+  if (upload(b.sphere_dirs, dirs, b.main) || upload(b.sphere_w, w, b.main)) return 1;
   // surface-radiance is called with ray-steps as its sphere steps (atmosphere_lut.clj:89)
   sphere_directions(P.shapes.ray_steps >> 2, P.shapes.ray_steps, kPi / 2, dirs, w);  // sphere.clj:96-99
   b.n_half = (int)w.size();
-  if (b.n_half > 0 && (upload(b.half_dirs, dirs) || upload(b.half_w, w))) return 1;
+  if (b.n_half > 0 && (upload(b.half_dirs, dirs, b.main) || upload(b.half_w, w, b.main))) return 1;
   if (dev_alloc(b.dir_info, (size_t)P.shapes.s4[0] * b.n_sphere)) return 1;
   if (dev_alloc(b.tiles_a, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
   if (dev_alloc(b.tiles_b, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
@@ -286,19 +294,19 @@ static int stage_begin(Builder &b, const std::string &name) {
     CUDA_TRY(cudaEventCreate(&s.end));
     b.stages.push_back(s);
   }
-  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].begin, g_stream));
+  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].begin, b.main));
   return 0;
 }
 
 static int stage_end(Builder &b) {
-  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, g_stream));
+  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, b.main));
   b.stage_cursor++;
   return 0;
 }
 
 static int peer_barrier(Builder &b) {
   b.epoch++;
-  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 0, b.rank, b.world, b.epoch, b.error_flag, g_stream));
+  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 0, b.rank, b.world, b.epoch, b.error_flag, b.main));
   b.launches++;
   return 0;
 }
@@ -327,7 +335,7 @@ static int gather(Builder &b, float4 *table) {
   if (b.p2p) return peer_barrier(b);   // the kernel already stored this rank's texels on every GPU
   if (!b.allgather) return 0;
   size_t bytes = (size_t)b.he_per_rank * b.ntex * sizeof(float4);
-  if (b.allgather(b.allgather_user, table, bytes, (void *)g_stream)) return fail("allgather callback failed");
+  if (b.allgather(b.allgather_user, table, bytes, (void *)b.main)) return fail("allgather callback failed");
   return 0;
 }
 
@@ -372,7 +380,8 @@ static int order_after(Builder &b, size_t &cursor, cudaStream_t from, cudaStream
 // dS and dE are double buffered so the side stream can still read order n-1 while order n is written.
 static int builder_run(Builder &b) {
   const Params &P = b.P;
-  cudaStream_t st = g_stream, side = b.side;
+  CUDA_TRY(cudaSetDevice(b.device));
+  cudaStream_t st = b.main, side = b.side;
   b.stage_cursor = 0;
   b.launches = 0;
   size_t ev = 0;
@@ -528,14 +537,21 @@ extern "C" int atmlut_init(int device) {
 
 namespace {
 void drop_generate_cache();
+void drop_multi_cache();
 }
 
 extern "C" void *atmlut_stream(void) { return (void *)g_stream; }
 
 extern "C" void atmlut_destroy(void) {
   drop_generate_cache();
-  if (g_exp_table) cudaFree(g_exp_table);
-  g_exp_table = nullptr;
+  drop_multi_cache();
+  for (int d = 0; d < 64; d++)
+    if (g_exp_table[d]) {
+      cudaSetDevice(d);
+      cudaFree(g_exp_table[d]);
+      g_exp_table[d] = nullptr;
+    }
+  if (g_device >= 0) cudaSetDevice(g_device);
   if (g_stream) {
     cudaStreamSynchronize(g_stream);
     cudaStreamDestroy(g_stream);
@@ -583,6 +599,8 @@ extern "C" int atmlut_builder_create(const atmlut_planet *planet, const atmlut_s
   b->iterations = cfg->iterations;
   b->rank = rank;
   b->world = world;
+  b->device = g_device;
+  b->main = g_stream;
   if (builder_alloc(*b)) {
     delete b;
     return 1;
@@ -671,9 +689,11 @@ extern "C" int atmlut_builder_run(void *builder) {
 }
 
 extern "C" int atmlut_builder_sync(void *builder) {
-  CUDA_TRY(cudaStreamSynchronize(g_stream));
-  if (builder) return check_peer_error((Builder *)builder);
-  return 0;
+  if (!builder) return fail("builder is NULL");
+  Builder *b = (Builder *)builder;
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->main));
+  return check_peer_error(b);
 }
 
 extern "C" int atmlut_builder_download(void *builder, float *transmittance, float *surface_radiance,
@@ -681,15 +701,16 @@ extern "C" int atmlut_builder_download(void *builder, float *transmittance, floa
   if (!builder) return fail("builder is NULL");
   Builder *b = (Builder *)builder;
   if (!b->ran) return fail("builder has not run");
+  CUDA_TRY(cudaSetDevice(b->device));
   if (transmittance)
-    CUDA_TRY(cudaMemcpyAsync(transmittance, b->file_T, (size_t)b->nt * 12, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(transmittance, b->file_T, (size_t)b->nt * 12, cudaMemcpyDeviceToHost, b->main));
   if (surface_radiance)
-    CUDA_TRY(cudaMemcpyAsync(surface_radiance, b->file_E, (size_t)b->ne * 12, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(surface_radiance, b->file_E, (size_t)b->ne * 12, cudaMemcpyDeviceToHost, b->main));
   if (ray_scatter)
-    CUDA_TRY(cudaMemcpyAsync(ray_scatter, b->file_S, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(ray_scatter, b->file_S, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, b->main));
   if (mie_strength)
-    CUDA_TRY(cudaMemcpyAsync(mie_strength, b->file_M, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, g_stream));
-  CUDA_TRY(cudaStreamSynchronize(g_stream));
+    CUDA_TRY(cudaMemcpyAsync(mie_strength, b->file_M, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, b->main));
+  CUDA_TRY(cudaStreamSynchronize(b->main));
   return check_peer_error(b);
 }
 
@@ -716,8 +737,8 @@ extern "C" int atmlut_builder_work(void *builder, double *esamples, double *look
   Builder *b = (Builder *)builder;
   if (!b || !b->ran) return fail("builder has not run");
   unsigned long long c[2];
-  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, g_stream));
-  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, b->main));
+  CUDA_TRY(cudaStreamSynchronize(b->main));
   std::vector<DirInfo> info((size_t)b->P.shapes.s4[0] * b->n_sphere);
   CUDA_TRY(cudaMemcpy(info.data(), b->dir_info, info.size() * sizeof(DirInfo), cudaMemcpyDeviceToHost));
   const Params &P = b->P;
@@ -748,16 +769,19 @@ extern "C" int atmlut_builder_counter(void *builder, int which, double *value) {
   }
   if (which < 0 || which > 2) return fail("which must be 0, 1 or 2");
   unsigned long long c[2];
-  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, g_stream));
-  CUDA_TRY(cudaStreamSynchronize(g_stream));
+  CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, b->main));
+  CUDA_TRY(cudaStreamSynchronize(b->main));
   *value = (double)c[which];
   return 0;
 }
 
 extern "C" int atmlut_builder_destroy(void *builder) {
   if (!builder) return 0;
-  cudaStreamSynchronize(g_stream);
-  delete (Builder *)builder;
+  Builder *b = (Builder *)builder;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->main);
+  delete b;
+  if (g_device >= 0) cudaSetDevice(g_device);
   return 0;
 }
 
@@ -798,6 +822,117 @@ extern "C" int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter
   int rc = atmlut_builder_run(g_cache.builder);
   if (!rc) rc = atmlut_builder_download(g_cache.builder, transmittance, surface_radiance, ray_scatter, mie_strength);
   if (rc) drop_generate_cache();
+  return rc;
+}
+
+// ------------------------------------------------------------------ C ABI: one process, several GPUs
+
+// A host that cannot run one process per GPU (the JVM behind `clj -T:build`) drives all GPUs of the box from
+// this single call.  Same peer-to-peer scheme as the multi-process mode (interleaved pairs, every finished
+// texel stored into every GPU's tables, flag barriers), but the peer pointers come from
+// cudaDeviceEnablePeerAccess instead of CUDA IPC, and one host thread enqueues every GPU's DAG in turn --
+// nothing blocks on the host until the final synchronisation.
+namespace {
+
+struct MultiCache {
+  std::vector<Builder *> group;
+  atmlut_planet planet;
+  atmlut_scatter scatter[2];
+  atmlut_config cfg;
+} g_multi;
+
+void drop_multi_cache() {
+  for (Builder *b : g_multi.group) atmlut_builder_destroy(b);
+  g_multi.group.clear();
+}
+
+int create_group(const atmlut_planet *planet, const atmlut_scatter *scatter, const atmlut_config *cfg, int num_gpus,
+                 std::vector<Builder *> &group) {
+  for (int d = 0; d < num_gpus; d++) {
+    CUDA_TRY(cudaSetDevice(d));
+    Builder *b = new Builder();
+    group.push_back(b);
+    b->device = d;
+    b->own_main = true;
+    if (make_params(planet, scatter, 2, cfg, b->P)) return 1;
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking));
+    b->iterations = cfg->iterations;
+    b->rank = d;
+    b->world = num_gpus;
+    if (builder_alloc(*b)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(b->main));
+  }
+  for (int d = 0; d < num_gpus; d++) {
+    CUDA_TRY(cudaSetDevice(d));
+    for (int q = 0; q < num_gpus; q++) {
+      if (q == d) continue;
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, d, q));
+      if (!can) return fail("GPUs without peer access cannot share one build");
+      cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled)
+        cudaGetLastError();
+      else if (e != cudaSuccess)
+        return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+    }
+  }
+  for (int d = 0; d < num_gpus; d++) {
+    Builder *b = group[d];
+    for (int q = 0; q < num_gpus; q++) {
+      Builder *o = group[q];
+      if (q != d) {
+        b->peer_R1.p[b->peer_R1.n++] = o->R1;
+        b->peer_M1.p[b->peer_M1.n++] = o->M1;
+        b->peer_dJ.p[b->peer_dJ.n++] = o->dJ;
+        b->peer_dS.p[b->peer_dS.n++] = o->dS;
+        b->peer_dS2.p[b->peer_dS2.n++] = o->dS2;
+        b->peer_S.p[b->peer_S.n++] = o->S;
+        b->peer_S_new.p[b->peer_S_new.n++] = o->S_new;
+      }
+      b->peer_flags[q] = o->flags;
+    }
+    b->p2p = true;
+    b->he_stride = num_gpus;
+    b->he_begin = d;
+    b->he_count = b->n_he > d ? (b->n_he - d + num_gpus - 1) / num_gpus : 0;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
+                                     const atmlut_config *cfg, int num_gpus, float *transmittance,
+                                     float *surface_radiance, float *ray_scatter, float *mie_strength) {
+  if (num_gpus == 1)
+    return atmlut_generate(planet, scatter, n, cfg, transmittance, surface_radiance, ray_scatter, mie_strength);
+  if (!planet || !scatter || !cfg) return fail("planet, scatter and config must not be NULL");
+  if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
+  if (num_gpus < 1 || num_gpus > kMaxPeers || num_gpus > atmlut_device_count())
+    return fail("num_gpus must be between 1 and min(8, number of CUDA devices)");
+  if (cfg->iterations < 0) return fail("iterations must not be negative");
+  const bool hit = (int)g_multi.group.size() == num_gpus && !memcmp(&g_multi.planet, planet, sizeof *planet) &&
+                   !memcmp(g_multi.scatter, scatter, 2 * sizeof *scatter) && !memcmp(&g_multi.cfg, cfg, sizeof *cfg);
+  if (!hit) {
+    drop_multi_cache();
+    if (create_group(planet, scatter, cfg, num_gpus, g_multi.group)) {
+      drop_multi_cache();
+      return 1;
+    }
+    g_multi.planet = *planet;
+    g_multi.scatter[0] = scatter[0];
+    g_multi.scatter[1] = scatter[1];
+    g_multi.cfg = *cfg;
+  }
+  int rc = 0;
+  for (Builder *b : g_multi.group)
+    if (!rc) rc = builder_run(*b);
+  for (Builder *b : g_multi.group)
+    if (!rc) rc = atmlut_builder_sync(b);
+  if (!rc)
+    rc = atmlut_builder_download(g_multi.group[0], transmittance, surface_radiance, ray_scatter, mie_strength);
+  if (rc) drop_multi_cache();
+  if (g_device >= 0) cudaSetDevice(g_device);
   return rc;
 }
 
