@@ -225,11 +225,16 @@ __device__ __forceinline__ void fill_exp_tab(double *tab, const double *global_t
 
 // atmosphere.clj:322-326 for lookups inside the integration kernels, from the sine of the sun elevation.
 // sin <= -0.2 is below the table's range: the reference's max(0, .) gives exactly 0 there.
-__device__ __forceinline__ double sun_elevation_coord(const double *exp_table, int size, double sin_elevation) {
-  const double inv = 1.0 / (1 - 0.02732372244729256);   // 1 / (1 - exp(-3.6))
-  const double y = fmax(0 - 3 * sin_elevation - 0.6, -4.0);
+// `scale` = (size - 1) / (1 - exp(-3.6)), hoisted by the caller.  Plain compares instead of fmax/fmin: the
+// operands are never NaN here and the IEEE min/max sequences cost twice as many instructions in double.
+__device__ __forceinline__ double sun_elevation_scale(int size) { return (double)(size - 1) / (1 - 0.02732372244729256); }
+
+__device__ __forceinline__ double sun_elevation_coord(const double *exp_table, double scale, double sin_elevation) {
+  double y = 0 - 3 * sin_elevation - 0.6;
   if (y >= 0.0) return 0.0;
-  return (double)(size - 1) * fmax(0.0, (1 - exp_tab(exp_table, y)) * inv);
+  y = y < -4.0 ? -4.0 : y;                 // table range (|sin| <= 1 gives y >= -3.6)
+  const double c = (1 - exp_tab(exp_table, y)) * scale;
+  return c < 0.0 ? 0.0 : c;
 }
 
 // ------------------------------------------------------------------ float4 table lookups
@@ -253,6 +258,17 @@ __device__ __forceinline__ Axis axis_from(float c, int n) {
 __device__ __forceinline__ Axis axis_from(double c, int n) {
   double i = fmin(fmax(c, 0.0), (double)(n - 1));
   double u = floor(i);
+  Axis a;
+  a.u = (int)u;
+  a.v = min(a.u + 1, n - 1);
+  a.s = (float)(i - u);
+  return a;
+}
+
+// interpolate.clj:75-98 for a coordinate known to be >= 0 and not NaN: clip to n - 1, floor, fraction
+__device__ __forceinline__ Axis axis_from_nonneg(double c, int n, double nmax) {
+  const double i = c < nmax ? c : nmax;
+  const double u = floor(i);
   Axis a;
   a.u = (int)u;
   a.v = min(a.u + 1, n - 1);

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
 // ------------------------------------------------------------------ K6: ray scatter from the dJ table
 
 struct alignas(16) LookupSmem {
-  int row[kMaxSteps][4];       // element offsets of the (height, elevation) corner tiles (hu,eu) (hu,ev) (hv,eu) (hv,ev)
+  long long row[kMaxSteps][4]; // byte offsets of the (height, elevation) corner tiles (hu,eu) (hu,ev) (hv,eu) (hv,ev)
   float hs[kMaxSteps], es[kMaxSteps];
   float tr[kMaxSteps][3];      // T(x -> p_k)
   double rk[kMaxSteps];        // |p_k|
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     V3 p = v3(vs.pkx[k], vs.pky[k], 0.0);
     Axis ah = axis_from(height_to_index(P.planet, H, p), H);
     Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
-    const int tile_elems = S * A;
-    ls.row[k][0] = (ah.u * E + ae.u) * tile_elems;
-    ls.row[k][1] = (ah.u * E + ae.v) * tile_elems;
-    ls.row[k][2] = (ah.v * E + ae.u) * tile_elems;
-    ls.row[k][3] = (ah.v * E + ae.v) * tile_elems;
+    const long long tile_bytes = (long long)S * A * sizeof(float4);
+    ls.row[k][0] = (ah.u * E + ae.u) * tile_bytes;
+    ls.row[k][1] = (ah.u * E + ae.v) * tile_bytes;
+    ls.row[k][2] = (ah.v * E + ae.u) * tile_bytes;
+    ls.row[k][3] = (ah.v * E + ae.v) * tile_bytes;
     ls.hs[k] = ah.s;
     ls.es[k] = ae.s;
     float tr[3];
@@ -364,13 +364,14 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     const bool one_per_thread = ntex <= (int)blockDim.x;
     const bool loader = (int)threadIdx.x < ntex;
     float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+    const char *dj_mine = reinterpret_cast<const char *>(dj + threadIdx.x);
     if (one_per_thread && loader) {
-      const int4 rows = *reinterpret_cast<const int4 *>(ls.row[0]);
-      c00 = ldg4(dj + rows.x + threadIdx.x);
-      c01 = ldg4(dj + rows.y + threadIdx.x);
-      c10 = ldg4(dj + rows.z + threadIdx.x);
-      c11 = ldg4(dj + rows.w + threadIdx.x);
+      c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][0]));
+      c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][1]));
+      c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][2]));
+      c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][3]));
     }
+    const double sun_scale = sun_elevation_scale(S), s_max = (double)(S - 1);
     for (int k = 0; k < steps; k++) {
       float4 *tile = tiles + (size_t)(k & 1) * ntex;
       {
@@ -378,19 +379,21 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         if (one_per_thread) {
           if (loader) tile[threadIdx.x] = mix4(mix4(c00, c01, es), mix4(c10, c11, es), hs);
         } else {
-          const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k]);
-          const float4 *t00 = dj + rows.x, *t01 = dj + rows.y, *t10 = dj + rows.z, *t11 = dj + rows.w;
+          const char *base = reinterpret_cast<const char *>(dj);
+          const float4 *t00 = reinterpret_cast<const float4 *>(base + ls.row[k][0]);
+          const float4 *t01 = reinterpret_cast<const float4 *>(base + ls.row[k][1]);
+          const float4 *t10 = reinterpret_cast<const float4 *>(base + ls.row[k][2]);
+          const float4 *t11 = reinterpret_cast<const float4 *>(base + ls.row[k][3]);
           for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
             tile[idx] = mix4(mix4(ldg4(t00 + idx), ldg4(t01 + idx), es), mix4(ldg4(t10 + idx), ldg4(t11 + idx), es), hs);
         }
       }
       __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
       if (one_per_thread && loader && k + 1 < steps) {
-        const int4 rows = *reinterpret_cast<const int4 *>(ls.row[k + 1]);
-        c00 = ldg4(dj + rows.x + threadIdx.x);
-        c01 = ldg4(dj + rows.y + threadIdx.x);
-        c10 = ldg4(dj + rows.z + threadIdx.x);
-        c11 = ldg4(dj + rows.w + threadIdx.x);
+        c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][0]));
+        c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][1]));
+        c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][2]));
+        c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][3]));
       }
       if (active) {
         // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         // that rows the reference clamps to exactly 0 are clamped here as well.
         double sin_elev = l.x * ls.nx[k] + l.y * ls.ny[k];
         if (sin_elev < -0.2 + 1e-9) sin_elev = (l.x * vs.pkx[k] + l.y * vs.pky[k]) / ls.rk[k];
-        const Axis as = axis_from(sun_elevation_coord(ls.exp_table, S, sin_elev), S);
+        const Axis as = axis_from_nonneg(sun_elevation_coord(ls.exp_table, sun_scale, sin_elev), S, s_max);
         const float4 j = lookup2_smem(tile, A, as, aa);
         acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
         acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
@@ -553,6 +556,8 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
   const int ntex = S * A;
   const size_t tile_base = (size_t)h * ndirs * ntex;
   const float phase_c0 = (float)((3.0 * (1.0 - phase_g * phase_g)) / (8.0 * kPi * (2.0 + phase_g * phase_g)));
+  const double e_scale = sun_elevation_scale(P.shapes.se[1]), e_max = (double)(P.shapes.se[1] - 1);
+  const double a_half = 0.5 * (double)(A - 1), a_max = (double)(A - 1);
   for (int texel = threadIdx.x; texel < ntex; texel += blockDim.x) {
     const int si = texel / A, ai = texel % A;
     double ss = index_to_sin_sun_elevation(S, (double)si);
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
         // lower clamp it is recomputed as the reference writes it, (dot point l) / (mag point)
         double sin_elev = r.ux * l.x + r.uy * l.y + r.uz * l.z;
         if (sin_elev < -0.2 + 1e-9) sin_elev = (r.px * l.x + r.py * l.y + r.pz * l.z) / r.pm;
-        Axis es = axis_from(sun_elevation_coord(s_exp, P.shapes.se[1], sin_elev), P.shapes.se[1]);
+        Axis es = axis_from_nonneg(sun_elevation_coord(s_exp, e_scale, sin_elev), P.shapes.se[1], e_max);
         float4 ev = lookup2(de, P.shapes.se[1], eh, es);
         s.x = fmaf(r.tb[0], ev.x, s.x);
         s.y = fmaf(r.tb[1], ev.y, s.y);
