@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
     for (int d = 0; d < ndirs; d++) {
       const PointDir &r = pd[d];
       const double mu = r.ox * l.x + r.oy * l.y + r.oz * l.z;
-      const Axis aa = axis_from((double)(A - 1) * ((1 + mu) / 2), A);
+      const double ca = a_half * (1 + mu);   // sun-angle-to-index (atmosphere.clj:368-372); continuous coordinate
+      const Axis aa = axis_from_nonneg(ca < 0.0 ? 0.0 : ca, A, a_max);
       float4 s = lookup2(tiles_a + tile_base + (size_t)d * ntex, A, as, aa);
       if (tiles_b) {
         float4 m = lookup2(tiles_b + tile_base + (size_t)d * ntex, A, as, aa);
