@@ -150,7 +150,7 @@ __global__ void k_surface_radiance_base(Params P, float4 *out) {
 // acc_c[ch] = sum over outer samples k in [k0, k1) of
 //   exp(-h(p_k)/scale_c) T(x->p_k)[ch] T(p_k->sun)[ch] [sun visible from p_k]
 // for the texel with light direction l (atmosphere.clj:192-200 with the first-order sources :140-182).
-__device__ __forceinline__ void first_order_texel(const Params &P, const ViewSmem &vs, V3 l, int k0, int k1,
+__device__ __forceinline__ void first_order_texel(const Params &P, const ViewSmem &vs, V3 l, int k0, int k1, int kstride,
                                                   float acc0[3], float acc1[3], unsigned &esamples) {
   const int steps = P.shapes.ray_steps;
   const double rt2 = sqr(P.planet.radius + P.planet.height);
@@ -159,7 +159,7 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
   const double ll = dot(l, l);
   const double llen = sqrt(ll);
   const double inv_ll = 1.0 / ll;   // the end point of the sun ray only places samples; an ulp there is harmless
-  for (int k = k0; k < k1; k++) {
+  for (int k = k0; k < k1; k += kstride) {
     const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
     const double pl = l.x * pkx + l.y * pky;
     // filtered-sun-light (atmosphere.clj:154-160): is-above-horizon? (p_k, l)
@@ -242,16 +242,32 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_warps = nchunks * nwarps;            // warps serving this pair
     const int wg = chunk * nwarps + warp;
-    const int ngroups = (ntex + 31) >> 5;
+    // Lane layout.  Whether the sun is visible from p_k depends mostly on the light-elevation row and on k, and
+    // visible k form an interval.  With narrow rows (A headings, A a power of two below 32) a warp therefore takes
+    // ONE row and spreads the outer samples over 32 / A lane groups, k interleaved (k = q, q + 32/A, ...): lanes
+    // then agree on visibility almost always.  Wide or odd rows fall back to 32 consecutive texels per warp.
+    const bool row_layout = A < 32 && (A & (A - 1)) == 0;
+    const int kq = row_layout ? 32 / A : 1;
+    const int ngroups = row_layout ? S : (ntex + 31) >> 5;
     for (int pass = 0; pass < passes; pass++) {
       const int group = pass * total_warps + ((pass & 1) ? total_warps - 1 - wg : wg);
-      const int texel = group * 32 + lane;
+      const int texel = row_layout ? group * A + (lane & (A - 1)) : group * 32 + lane;
       if (group >= ngroups || texel >= ntex) continue;
       const int si = texel / A, ai = texel % A;
       const double ss = index_to_sin_sun_elevation(S, (double)si);
       const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
       float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
-      first_order_texel(P, vs, l, 0, steps, acc0, acc1, esamples);
+      first_order_texel(P, vs, l, row_layout ? lane / A : 0, steps, kq, acc0, acc1, esamples);
+      if (kq > 1) {
+        for (int o = A; o < 32; o <<= 1) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            acc0[ch] += __shfl_xor_sync(0xffffffffu, acc0[ch], o);
+            acc1[ch] += __shfl_xor_sync(0xffffffffu, acc1[ch], o);
+          }
+        }
+        if (lane >= A) continue;
+      }
       first_order_store(P, ray, v, l, (size_t)he * ntex + texel, acc0, acc1, oa, ob);
     }
   } else {
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
       const double ss = index_to_sin_sun_elevation(S, (double)si);
       l = index_to_sun_direction(A, v, ss, (double)ai);
       const int k0 = (int)(((long long)steps * part) / kparts), k1 = (int)(((long long)steps * (part + 1)) / kparts);
-      first_order_texel(P, vs, l, k0, k1, acc0, acc1, esamples);
+      first_order_texel(P, vs, l, k0, k1, 1, acc0, acc1, esamples);
     }
     __syncthreads();
 #pragma unroll
@@ -821,14 +837,16 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
   static const int warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
-  static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 1));
+  static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 4));
   const int threads = warps * 32;
   const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
   int kparts = 1, passes = 1, nchunks = 1;
   if (ntex < threads) {
     kparts = std::min(P.shapes.ray_steps, threads / ntex);
   } else {
-    const int ngroups = (ntex + 31) / 32;
+    const int A = P.shapes.s4[3];
+    const bool row_layout = A < 32 && (A & (A - 1)) == 0;     // must match the kernel
+    const int ngroups = row_layout ? P.shapes.s4[2] : (ntex + 31) / 32;
     passes = std::min(want_passes, (ngroups + warps - 1) / warps);
     const int total_warps = (ngroups + passes - 1) / passes;
     nchunks = (total_warps + warps - 1) / warps;
