@@ -24,7 +24,6 @@ import ctypes
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -336,7 +335,11 @@ def run_b200(args):
                 "stage_ms": {k: round(v, 4) for k, v in stage_dict.items()},
                 "stage_ms_max_over_ranks": {k: round(max(r[k] for r in all_stages), 4) for k in my_stages},
                 "stage_ms_min_over_ranks": {k: round(min(r[k] for r in all_stages), 4) for k in my_stages},
-                "work_per_step": work, "roofline": roofline}
+                "work_per_step": work, "roofline": roofline,
+                "lookup_kernels": {
+                    "note": "issue-slot / FP64 bound gather kernels; no single-pipe roofline applies (ncu: profiles/)",
+                    "ray_scatter_lookups_per_s": (n4 / world) * 100 * cfg.iterations / max(stage_dict.get("ray_scatter", 0.0) * 1e-3, 1e-12),
+                    "point_scatter_direction_evals_per_s": (n4 / world) * 71 * cfg.iterations / max(stage_dict.get("point_scatter", 0.0) * 1e-3, 1e-12)}}
         if not args.no_cpu_baseline and world == 1 and args.workload == "shipped":
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         print(json.dumps(line), flush=True)

@@ -60,11 +60,6 @@ def _pts(a):
     return a
 
 
-def _single(fn, *arrays):
-    """Call a batch function with single items and unwrap."""
-    return fn(*arrays)[0]
-
-
 class FirstOrder:
     """First-order point-scatter functions of atmosphere.clj:170-189 bound to their leading arguments, i.e.
     (partial point-scatter-component planet scatter component steps intensity) and friends."""

@@ -192,7 +192,6 @@ struct Builder {
   std::vector<Stage> stages;
   size_t stage_cursor = 0;
   bool ran = false;
-  double esamples = 0, lookups4d = 0, lookups2d = 0;
   long long launches = 0;   // kernels launched by the last run
 
   ~Builder() {
