@@ -83,6 +83,10 @@ int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_scatter *sca
 typedef int (*atmlut_allgather_fn)(void *user, void *device_buf, size_t bytes_per_rank, void *stream);
 int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
                           const atmlut_config *cfg, int rank, int world, void **builder);
+/* host-only helper: the quadrature directions (double[n][3]) and weights the sphere kernels use for table points
+ * (normal (1,0,0)); half = 0: integral-sphere(steps) sphere.clj:102-105, half = 1: integral-half-sphere(steps)
+ * sphere.clj:96-99.  Returns the number of directions (call with NULL pointers to size), -1 on error. */
+int atmlut_sphere_directions(int steps, int half, double *dirs, double *weights, int capacity);
 /* the partition: rank owns (height, elevation) pairs [begin, begin + count) of n_pairs = height_size *
  * elevation_size, padded to per_rank pairs per rank (host-only helper, needs no device) */
 int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank);

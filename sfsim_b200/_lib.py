@@ -56,7 +56,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void
 EXPORTS = [
     "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate", "atmlut_generate_multi",
-    "atmlut_builder_create", "atmlut_slab", "atmlut_builder_ipc_export", "atmlut_builder_ipc_import",
+    "atmlut_builder_create", "atmlut_sphere_directions", "atmlut_slab", "atmlut_builder_ipc_export", "atmlut_builder_ipc_import",
     "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
     "atmlut_builder_download", "atmlut_builder_stage_count", "atmlut_builder_stage_name", "atmlut_builder_stage_ms",
     "atmlut_builder_work", "atmlut_builder_counter", "atmlut_builder_destroy",

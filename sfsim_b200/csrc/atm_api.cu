@@ -608,6 +608,24 @@ extern "C" int atmlut_builder_create(const atmlut_planet *planet, const atmlut_s
   return 0;
 }
 
+// Host-only: the direction/weight list of integral-sphere (half = 0) or integral-half-sphere (half = 1) for the
+// normal (1, 0, 0) of every table point, exactly as the kernels receive it.  Call with dirs = NULL to size.
+extern "C" int atmlut_sphere_directions(int steps, int half, double *dirs, double *weights, int capacity) {
+  if (steps < 1) return -1;
+  std::vector<double> d, w;
+  if (half)
+    sphere_directions(steps >> 2, steps, kPi / 2, d, w);   // sphere.clj:96-99
+  else
+    sphere_directions(steps >> 1, steps, kPi, d, w);       // sphere.clj:102-105
+  const int n = (int)w.size();
+  if (dirs && weights) {
+    if (capacity < n) return -1;
+    memcpy(dirs, d.data(), d.size() * sizeof(double));
+    memcpy(weights, w.data(), w.size() * sizeof(double));
+  }
+  return n;
+}
+
 extern "C" int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank) {
   if (n_pairs < 0 || world < 1 || rank < 0 || rank >= world || !begin || !count || !per_rank)
     return fail("invalid argument");

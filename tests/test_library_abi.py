@@ -94,6 +94,24 @@ def test_convert_4d_to_2d_host_helper():
     np.testing.assert_array_equal(convert(t, 3), orc.convert_4d_to_2d(t.astype(np.float64)).astype(np.float32))
 
 
+def test_quadrature_tables_match_the_oracle():
+    """sphere.clj:70-105: the direction lists the kernels integrate over are the reference's, bit for bit
+    (ring counts ceil(sin(theta) * steps) sit on an integer at theta = pi/2)."""
+    lib = _lib.load()
+    for steps, half, theta_steps, theta_range in [(15, 0, 7, np.pi), (100, 1, 25, np.pi / 2), (6, 0, 3, np.pi),
+                                                  (64, 0, 32, np.pi), (64, 1, 16, np.pi / 2), (7, 1, 1, np.pi / 2)]:
+        n = lib.atmlut_sphere_directions(steps, half, None, None, 0)
+        dirs = np.zeros((n, 3))
+        weights = np.zeros(n)
+        assert lib.atmlut_sphere_directions(steps, half, _lib.ptr(dirs), _lib.ptr(weights), n) == n
+        want_dirs, want_w = orc.sphere_directions(theta_steps, steps, theta_range, (1, 0, 0))
+        assert n == len(want_w)
+        np.testing.assert_array_equal(dirs, want_dirs)
+        np.testing.assert_array_equal(weights, want_w)
+    assert lib.atmlut_sphere_directions(15, 0, None, None, 0) == 71          # SURVEY.md App. A.3
+    assert lib.atmlut_sphere_directions(100, 1, None, None, 0) == 1605
+
+
 def test_slab_partition():
     """N4 pairs split in equal contiguous slabs; the library and its mirror agree."""
     for n_pairs in (4064, 16256, 7, 1, 250):
