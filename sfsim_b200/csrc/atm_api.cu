@@ -802,6 +802,27 @@ extern "C" int atmlut_builder_destroy(void *builder) {
   return 0;
 }
 
+// field-wise equality of the parameter structs (memcmp would also compare padding bytes)
+static bool same_inputs(const atmlut_planet &pa, const atmlut_scatter *sa, const atmlut_config &ca,
+                        const atmlut_planet &pb, const atmlut_scatter *sb, const atmlut_config &cb) {
+  for (int i = 0; i < 3; i++)
+    if (pa.centre[i] != pb.centre[i] || pa.brightness[i] != pb.brightness[i] || ca.intensity[i] != cb.intensity[i])
+      return false;
+  if (pa.radius != pb.radius || pa.height != pb.height) return false;
+  for (int c = 0; c < 2; c++) {
+    for (int i = 0; i < 3; i++)
+      if (sa[c].base[i] != sb[c].base[i]) return false;
+    if (sa[c].scale != sb[c].scale || sa[c].g != sb[c].g || sa[c].quotient != sb[c].quotient) return false;
+  }
+  return ca.height_size == cb.height_size && ca.elevation_size == cb.elevation_size &&
+         ca.light_elevation_size == cb.light_elevation_size && ca.heading_size == cb.heading_size &&
+         ca.transmittance_height_size == cb.transmittance_height_size &&
+         ca.transmittance_elevation_size == cb.transmittance_elevation_size &&
+         ca.surface_height_size == cb.surface_height_size &&
+         ca.surface_sun_elevation_size == cb.surface_sun_elevation_size && ca.ray_steps == cb.ray_steps &&
+         ca.sphere_steps == cb.sphere_steps && ca.iterations == cb.iterations;
+}
+
 // The one-shot call keeps its builder (device tables, quadrature tables, events) between calls with
 // identical parameters, so a repeated build pays for kernels and the result copy only.
 namespace {
@@ -825,8 +846,8 @@ extern "C" int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter
   if (ensure_init()) return 1;
   if (!planet || !scatter || !cfg) return fail("planet, scatter and config must not be NULL");
   if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
-  const bool hit = g_cache.builder && g_cache.device == g_device && !memcmp(&g_cache.planet, planet, sizeof *planet) &&
-                   !memcmp(g_cache.scatter, scatter, 2 * sizeof *scatter) && !memcmp(&g_cache.cfg, cfg, sizeof *cfg);
+  const bool hit = g_cache.builder && g_cache.device == g_device &&
+                   same_inputs(g_cache.planet, g_cache.scatter, g_cache.cfg, *planet, scatter, *cfg);
   if (!hit) {
     drop_generate_cache();
     if (atmlut_builder_create(planet, scatter, n, cfg, 0, 1, &g_cache.builder)) return 1;
@@ -928,8 +949,8 @@ extern "C" int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_s
   if (num_gpus < 1 || num_gpus > kMaxPeers || num_gpus > atmlut_device_count())
     return fail("num_gpus must be between 1 and min(8, number of CUDA devices)");
   if (cfg->iterations < 0) return fail("iterations must not be negative");
-  const bool hit = (int)g_multi.group.size() == num_gpus && !memcmp(&g_multi.planet, planet, sizeof *planet) &&
-                   !memcmp(g_multi.scatter, scatter, 2 * sizeof *scatter) && !memcmp(&g_multi.cfg, cfg, sizeof *cfg);
+  const bool hit = (int)g_multi.group.size() == num_gpus &&
+                   same_inputs(g_multi.planet, g_multi.scatter, g_multi.cfg, *planet, scatter, *cfg);
   if (!hit) {
     drop_multi_cache();
     if (create_group(planet, scatter, cfg, num_gpus, g_multi.group)) {
