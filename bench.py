@@ -317,10 +317,31 @@ def run_b200(args):
             stage_dict[key] = stage_dict.get(key, 0.0) + ms
         launches_per_step = int(work["kernel_launches"])
         mufu_peak = peaks.get("mufu_ex2_per_s")
+        # DRAM traffic of one K3 launch from the committed `ncu --set full` capture, and the driver-measured HBM peak
+        traffic = None
+        try:
+            text = open(os.path.join(ROOT, "profiles", "r1_final_ncu_summary.txt")).read().split("== k_point_scatter")[0]
+            units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = 0.0
+            for line in text.splitlines():
+                if "dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line:
+                    parts = line.split()
+                    traffic += float(parts[1]) * units[parts[2]]
+        except Exception:
+            traffic = None
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
         if first_ms and work.get("esamples_first_order") and mufu_peak:
             achieved = 2.0 * work["esamples_first_order"] / (first_ms * 1e-3)
             roofline = {"bound": "sfu", "kernel": "k_first_order", "achieved": achieved / 1e9, "peak": mufu_peak / 1e9,
-                        "unit": "Gop/s (MUFU.EX2)", "frac": achieved / mufu_peak, "traffic": None,
+                        "unit": "Gop/s (MUFU.EX2)", "frac": achieved / mufu_peak, "traffic": traffic,
+                        "traffic_note": "dram read+write bytes of one launch, profiles/r1_final_ncu_summary.txt",
+                        "hbm": {"algorithmic_bytes": 2 * n4 // world * 16,
+                                "achieved_GBs": 2 * n4 / world * 16 / (first_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
+                                "note": "two float4 output tables per launch; the kernel is SFU-bound, not HBM-bound"},
                         "peak_source": "measured on this pool's B200 by tools/pipe_peaks.cu (profiles/pipe_peaks_b200.json)",
                         "algorithmic_units": "2 MUFU.EX2 per overall-extinction sample; samples counted on the device",
                         "esamples_per_launch": work["esamples_first_order"], "launch_ms": first_ms}
