@@ -214,6 +214,9 @@ def test_file_layout_is_convert_4d_to_2d(reduced_oracle):
     dict(shape4=(3, 7, 5, 3), shape_t=(4, 9), shape_e=(3, 5), ray_steps=7, sphere_steps=5),       # ragged, odd
     dict(shape4=(2, 5, 20, 16), shape_t=(3, 5), shape_e=(2, 3), ray_steps=16, sphere_steps=6),    # > 256 texels per pair
     dict(shape4=(4, 6, 3, 2), shape_t=(4, 6), shape_e=(3, 4), ray_steps=33, sphere_steps=9),      # even elevation size
+    dict(shape4=(2, 3, 64, 16), shape_t=(3, 5), shape_e=(2, 3), ray_steps=8, sphere_steps=4),     # 1024 texels per pair (stress layout)
+    dict(shape4=(2, 3, 40, 32), shape_t=(3, 5), shape_e=(2, 3), ray_steps=8, sphere_steps=4),     # 1280 > 1024: two chunks, wide rows
+    dict(shape4=(2, 3, 5, 6), shape_t=(3, 5), shape_e=(2, 3), ray_steps=9, sphere_steps=4),       # heading size not a power of two
 ])
 def test_small_and_ragged_shapes(case):
     pl = orc.planet(**orc.EARTH)
@@ -263,6 +266,10 @@ def test_invalid_arguments_raise():
         atmosphere_lut.generate_tables(cfg=_lib.make_config(ray_steps=0))
     with pytest.raises(_lib.AtmlutError):
         atmosphere_lut.generate_tables(cfg=_lib.make_config(height_size=1))
+    with pytest.raises(_lib.AtmlutError, match="6144"):
+        atmosphere_lut.generate_tables(cfg=_lib.make_config(ray_scatter_shape=(2, 2, 100, 100), iterations=0))
+    with pytest.raises(_lib.AtmlutError):
+        atmosphere_lut.generate_tables(cfg=_lib.make_config(ray_steps=300))
     with pytest.raises(_lib.AtmlutError):
         atmosphere_lut.generate_tables(planet=dict(atmosphere_lut.earth, centre=(1.0, 0.0, 0.0)),
                                        cfg=lib_config(REDUCED, iterations=0))
