@@ -309,12 +309,15 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
 
 // ------------------------------------------------------------------ K6: ray scatter from the dJ table
 
+// Per-sample constants of the ray-scatter kernel, packed so that every thread fetches them with as few
+// (broadcast) shared-memory instructions as possible -- the kernel is bound by shared-memory wavefronts.
 struct alignas(16) LookupSmem {
-  long long row[kMaxSteps][4]; // byte offsets of the (height, elevation) corner tiles (hu,eu) (hu,ev) (hv,eu) (hv,ev)
-  float hs[kMaxSteps], es[kMaxSteps];
-  float tr[kMaxSteps][3];      // T(x -> p_k)
-  double rk[kMaxSteps];        // |p_k|
-  double nx[kMaxSteps], ny[kMaxSteps];   // p_k / |p_k|
+  longlong2 row01[kMaxSteps];   // byte offsets of the (height, elevation) corner tiles (hu,eu), (hu,ev)
+  longlong2 row23[kMaxSteps];   //                                                       (hv,eu), (hv,ev)
+  float4 trw[kMaxSteps];        // T(x -> p_k) rgb, elevation weight es
+  double2 nxy[kMaxSteps];       // p_k / |p_k|
+  float hs[kMaxSteps];          // height weight
+  double rk[kMaxSteps];         // |p_k| (exact fallback next to the clamp)
   double exp_table[kExpTabSize + 3];     // exp(i/64), i = -256 .. 0 (exp_tab)
 };
 
@@ -348,20 +351,14 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     Axis ah = axis_from(height_to_index(P.planet, H, p), H);
     Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
     const long long tile_bytes = (long long)S * A * sizeof(float4);
-    ls.row[k][0] = (ah.u * E + ae.u) * tile_bytes;
-    ls.row[k][1] = (ah.u * E + ae.v) * tile_bytes;
-    ls.row[k][2] = (ah.v * E + ae.u) * tile_bytes;
-    ls.row[k][3] = (ah.v * E + ae.v) * tile_bytes;
+    ls.row01[k] = make_longlong2((ah.u * E + ae.u) * tile_bytes, (ah.u * E + ae.v) * tile_bytes);
+    ls.row23[k] = make_longlong2((ah.v * E + ae.u) * tile_bytes, (ah.v * E + ae.v) * tile_bytes);
     ls.hs[k] = ah.s;
-    ls.es[k] = ae.s;
     float tr[3];
     transmittance_rgb(P.fast, vs.cv0[k], vs.cv1[k], tr);
-    ls.tr[k][0] = tr[0];
-    ls.tr[k][1] = tr[1];
-    ls.tr[k][2] = tr[2];
+    ls.trw[k] = make_float4(tr[0], tr[1], tr[2], ae.s);
     ls.rk[k] = sqrt(vs.rk2[k]);
-    ls.nx[k] = vs.pkx[k] / ls.rk[k];
-    ls.ny[k] = vs.pky[k] / ls.rk[k];
+    ls.nxy[k] = make_double2(vs.pkx[k] / ls.rk[k], vs.pky[k] / ls.rk[k]);
   }
   __syncthreads();
   const int ntex = S * A;
@@ -382,34 +379,38 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     float4 c00 = make_float4(0.f, 0.f, 0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
     const char *dj_mine = reinterpret_cast<const char *>(dj + threadIdx.x);
     if (one_per_thread && loader) {
-      c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][0]));
-      c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][1]));
-      c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][2]));
-      c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[0][3]));
+      const longlong2 r01 = ls.row01[0], r23 = ls.row23[0];
+      c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r01.x));
+      c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r01.y));
+      c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r23.x));
+      c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r23.y));
     }
     const double sun_scale = sun_elevation_scale(S), s_max = (double)(S - 1);
     for (int k = 0; k < steps; k++) {
       float4 *tile = tiles + (size_t)(k & 1) * ntex;
+      const float4 trw = ls.trw[k];
       {
-        const float es = ls.es[k], hs = ls.hs[k];
+        const float es = trw.w, hs = ls.hs[k];
         if (one_per_thread) {
           if (loader) tile[threadIdx.x] = mix4(mix4(c00, c01, es), mix4(c10, c11, es), hs);
         } else {
           const char *base = reinterpret_cast<const char *>(dj);
-          const float4 *t00 = reinterpret_cast<const float4 *>(base + ls.row[k][0]);
-          const float4 *t01 = reinterpret_cast<const float4 *>(base + ls.row[k][1]);
-          const float4 *t10 = reinterpret_cast<const float4 *>(base + ls.row[k][2]);
-          const float4 *t11 = reinterpret_cast<const float4 *>(base + ls.row[k][3]);
+          const longlong2 r01 = ls.row01[k], r23 = ls.row23[k];
+          const float4 *t00 = reinterpret_cast<const float4 *>(base + r01.x);
+          const float4 *t01 = reinterpret_cast<const float4 *>(base + r01.y);
+          const float4 *t10 = reinterpret_cast<const float4 *>(base + r23.x);
+          const float4 *t11 = reinterpret_cast<const float4 *>(base + r23.y);
           for (int idx = threadIdx.x; idx < ntex; idx += blockDim.x)
             tile[idx] = mix4(mix4(ldg4(t00 + idx), ldg4(t01 + idx), es), mix4(ldg4(t10 + idx), ldg4(t11 + idx), es), hs);
         }
       }
       __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
       if (one_per_thread && loader && k + 1 < steps) {
-        c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][0]));
-        c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][1]));
-        c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][2]));
-        c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + ls.row[k + 1][3]));
+        const longlong2 r01 = ls.row01[k + 1], r23 = ls.row23[k + 1];
+        c00 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r01.x));
+        c01 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r01.y));
+        c10 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r23.x));
+        c11 = ldg4(reinterpret_cast<const float4 *>(dj_mine + r23.y));
       }
       if (active) {
         // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a
@@ -417,13 +418,14 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         // sin = l . (p_k / |p_k|) with the unit vector precomputed per sample; only next to the lower clamp
         // (sin = -0.2, coordinate 0) it is recomputed as the reference writes it, (dot p l) / (mag p), so
         // that rows the reference clamps to exactly 0 are clamped here as well.
-        double sin_elev = l.x * ls.nx[k] + l.y * ls.ny[k];
+        const double2 n = ls.nxy[k];
+        double sin_elev = l.x * n.x + l.y * n.y;
         if (sin_elev < -0.2 + 1e-9) sin_elev = (l.x * vs.pkx[k] + l.y * vs.pky[k]) / ls.rk[k];
         const Axis as = axis_from_nonneg(sun_elevation_coord(ls.exp_table, sun_scale, sin_elev), S, s_max);
         const float4 j = lookup2_smem(tile, A, as, aa);
-        acc[0] = fmaf(ls.tr[k][0], j.x, acc[0]);
-        acc[1] = fmaf(ls.tr[k][1], j.y, acc[1]);
-        acc[2] = fmaf(ls.tr[k][2], j.z, acc[2]);
+        acc[0] = fmaf(trw.x, j.x, acc[0]);
+        acc[1] = fmaf(trw.y, j.y, acc[1]);
+        acc[2] = fmaf(trw.z, j.z, acc[2]);
       }
     }
     if (active) store_all(out, (size_t)he * ntex + texel, make_float4(acc[0] * a, acc[1] * a, acc[2] * a, 0.0f));
