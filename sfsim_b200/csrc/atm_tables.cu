@@ -18,11 +18,16 @@
 #include "atm_device.cuh"
 #include "atm_tables.h"
 
+#ifndef ATMLUT_K4_UNROLL
+#define ATMLUT_K4_UNROLL 1
+#endif
 #ifndef ATMLUT_FO_MIN_BLOCKS
 #define ATMLUT_FO_MIN_BLOCKS 4
 #endif
 
 namespace atm {
+
+constexpr int kPointScatterUnroll = ATMLUT_K4_UNROLL;   // directions per trip of the point-scatter loop
 
 // ------------------------------------------------------------------ view ray shared by one CTA
 
@@ -582,6 +587,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, co
     V3 l = index_to_sun_direction(A, v, ss, (double)ai);
     const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
     float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll kPointScatterUnroll
     for (int d = 0; d < ndirs; d++) {
       const PointDir &r = pd[d];
       const double mu = r.ox * l.x + r.oy * l.y + r.oz * l.z;
