@@ -155,6 +155,28 @@ def test_resampled_transmittance(reduced_oracle):
     assert rel_err(lib.resample(2, rec["T"]), rec["LT"]) <= TOL
 
 
+def test_first_order_sample_count_matches_the_reference():
+    """The device counts every overall-extinction sample it evaluates.  The reference evaluates steps^2 view-ray
+    samples per TEXEL plus steps sun-ray samples per (texel, outer sample) from which the sun is visible; the kernel
+    evaluates the view ray once per (height, elevation) PAIR.  The sun-ray counts must agree exactly -- a bit-exact
+    check of every is-above-horizon? decision (atmosphere.clj:95-102,154-160) of the table."""
+    cfg = lib_config(REDUCED, iterations=0)
+    builder = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg)
+    builder.run()
+    builder.sync()
+    gpu = builder.work()["esamples_first_order"]
+    builder.close()
+    h, e, s, a = REDUCED["shape4"]
+    steps = REDUCED["ray_steps"]
+    orc.counters_reset()
+    orc.table_first_order(orc.planet(**orc.EARTH), [orc.scatter(**orc.MIE), orc.scatter(**orc.RAYLEIGH)],
+                          orc_config(REDUCED), orc.scatter(**orc.RAYLEIGH), 0)
+    ref = orc.counters_get()["esamples"]
+    sun_ref = ref - h * e * s * a * steps * steps
+    sun_gpu = gpu - h * e * steps * steps
+    assert sun_ref > 0 and sun_gpu == sun_ref
+
+
 # ---------------------------------------------------------------- whole build
 
 def test_generate_matches_oracle(reduced_oracle):

@@ -140,6 +140,19 @@ def test_no_cpu_fallback_without_a_device():
         atmosphere.transmittance(atmosphere_lut.earth, [atmosphere_lut.rayleigh], 10, (0, 6378000.0, 0), (0, 1, 0), True)
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """A C99 program includes the header, links the shared library and calls the host-only entry points
+    (what a JNI / FFM / cgo consumer does)."""
+    import subprocess
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", ROOT, "-lsfsim_atmosphere",
+                           "-Wl,-rpath," + ROOT])
+    out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "devices=" in out.stdout
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libsfsim_atmosphere.so"))
