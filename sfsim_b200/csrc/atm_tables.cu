@@ -513,8 +513,10 @@ struct alignas(16) PointDir {
   float ehs;
 };
 
-// dJ[i] = integral-sphere of overall-in-scattering * (S(x, omega, l, not surface) + surface term)
-__global__ void __launch_bounds__(256) k_point_scatter(Params P, Shard shard, const float4 *__restrict__ tiles_a,
+// dJ[i] = integral-sphere of overall-in-scattering * (S(x, omega, l, not surface) + surface term).
+// 64 registers (4 CTAs per SM): neutral on a full grid, but the 508 CTAs of an 8-GPU slab then fit in one wave
+// (every thread's serial work is the same 71 directions, so smaller CTAs would not shorten the wave).
+__global__ void __launch_bounds__(256, 4) k_point_scatter(Params P, Shard shard, const float4 *__restrict__ tiles_a,
                                                        const float4 *__restrict__ tiles_b, double phase_g,
                                                        const float4 *__restrict__ de,
                                                        const double *__restrict__ dirs,
@@ -835,6 +837,18 @@ cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStrea
   return cudaGetLastError();
 }
 
+static int env_int(const char *name, int fallback);
+
+// CTAs a launch should at least have before the work of a (height, elevation) pair is left in one CTA:
+// six waves of 4 CTAs on every SM of the current device
+static int small_grid_ctas() {
+  static const int forced = env_int("ATMLUT_MIN_CTAS", 0);
+  if (forced > 0) return forced;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return 6 * 4 * sms;
+}
+
 static int env_int(const char *name, int fallback) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : fallback;
@@ -856,8 +870,16 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
     const bool row_layout = A < 32 && (A & (A - 1)) == 0;     // must match the kernel
     const int ngroups = row_layout ? P.shapes.s4[2] : (ntex + 31) / 32;
     passes = std::min(want_passes, (ngroups + warps - 1) / warps);
-    const int total_warps = (ngroups + passes - 1) / passes;
-    nchunks = (total_warps + warps - 1) / warps;
+    // Small grids (one slab of a multi-GPU build, small tables): fewer row groups per warp, i.e. more and smaller
+    // CTAs per pair, until the launch spans several waves -- the repeated view-ray set-up (steps^2 samples per
+    // CTA) is cheaper than SMs idling behind the slowest CTA of a single wave.
+    const int min_ctas = small_grid_ctas();
+    for (;;) {
+      const int total_warps = (ngroups + passes - 1) / passes;
+      nchunks = (total_warps + warps - 1) / warps;
+      if ((long long)he_count * nchunks >= min_ctas || passes == 1) break;
+      passes = (passes + 1) / 2;
+    }
   }
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
   k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);
