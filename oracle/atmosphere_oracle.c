@@ -1023,3 +1023,38 @@ void orc_table_resample_sum_t(const orc_planet *planet, const orc_config *cfg, c
   }
   counters_flush();
 }
+
+/* g(i) = forward(backward(i)) of the three spaces: the map every re-tabulation goes through.
+ * out holds `dims` doubles per texel. */
+void orc_roundtrip_4d(const orc_planet *planet, const orc_config *cfg, double *out) {
+  long count = prod(cfg->shape4, 4);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < count; i++) {
+    double idx[4], x[3], v[3], l[3];
+    int above;
+    unravel(i, cfg->shape4, 4, idx);
+    orc_ray_scatter_backward(planet, cfg->shape4, idx[0], idx[1], idx[2], idx[3], x, v, l, &above);
+    orc_ray_scatter_forward(planet, cfg->shape4, x, v, l, above, out + 4 * i);
+  }
+}
+
+void orc_roundtrip_t(const orc_planet *planet, const orc_config *cfg, double *out) {
+  long count = prod(cfg->shape_t, 2);
+  for (long i = 0; i < count; i++) {
+    double idx[2], x[3], v[3];
+    int above;
+    unravel(i, cfg->shape_t, 2, idx);
+    orc_transmittance_backward(planet, cfg->shape_t, idx[0], idx[1], x, v, &above);
+    orc_transmittance_forward(planet, cfg->shape_t, x, v, above, out + 2 * i);
+  }
+}
+
+void orc_roundtrip_e(const orc_planet *planet, const orc_config *cfg, double *out) {
+  long count = prod(cfg->shape_e, 2);
+  for (long i = 0; i < count; i++) {
+    double idx[2], x[3], l[3];
+    unravel(i, cfg->shape_e, 2, idx);
+    orc_surface_radiance_backward(planet, cfg->shape_e, idx[0], idx[1], x, l);
+    orc_surface_radiance_forward(planet, cfg->shape_e, x, l, out + 2 * i);
+  }
+}

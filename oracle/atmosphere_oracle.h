@@ -177,6 +177,11 @@ void orc_table_resample_sum_e(const orc_planet *planet, const orc_config *cfg, c
 void orc_table_resample_sum_t(const orc_planet *planet, const orc_config *cfg, const double *const *tabs, int ntabs,
                               const long *indices, long count, double *out);
 
+/* g(i) = forward(backward(i)) for every texel of a space (dims doubles per texel) */
+void orc_roundtrip_4d(const orc_planet *planet, const orc_config *cfg, double *out);
+void orc_roundtrip_t(const orc_planet *planet, const orc_config *cfg, double *out);
+void orc_roundtrip_e(const orc_planet *planet, const orc_config *cfg, double *out);
+
 /* counters: overall-extinction evaluations ("E-samples") and table lookups since the last reset */
 void orc_counters_reset(void);
 void orc_counters_get(long long *esamples, long long *lookups4d, long long *lookups2d);

@@ -577,6 +577,16 @@ def table_resample_sum_t(pl, cfg, tabs, indices=None):
     return _resample("orc_table_resample_sum_t", pl, cfg, tabs, cfg.shape_t, indices)
 
 
+def roundtrip(pl, cfg, which):
+    """forward(backward(i)) for every texel of ray-scatter-space (which=0), surface-radiance-space (1) or
+    transmittance-space (2); returns an array of shape + (dims,)."""
+    shape = {0: tuple(cfg.shape4), 1: tuple(cfg.shape_e), 2: tuple(cfg.shape_t)}[which]
+    out = np.zeros(shape + (len(shape),))
+    fn = {0: "orc_roundtrip_4d", 1: "orc_roundtrip_e", 2: "orc_roundtrip_t"}[which]
+    getattr(lib(), fn)(C.byref(pl), C.byref(cfg), _tab_ptr(out))
+    return out
+
+
 def counters_reset():
     lib().orc_counters_reset()
 
