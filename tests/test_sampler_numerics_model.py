@@ -1,0 +1,126 @@
+"""Executable form of DESIGN.md section 3: a numpy model of the kernels' overall-extinction sampler.
+
+The hot loop of the CUDA kernels evaluates exp(-h/H_c) along a ray as
+    u   = (|q|^2 - R'^2) / R'^2            in float64 (quadratic in the sample index, forward differences)
+    uf  = float32(u)                        by truncation (bit manipulation on the device)
+    h'  = R' * uf * (1/2 - uf/8 + uf^2/16 - 5 uf^3/128 + 7 uf^4/256)     in float32 (FMA chain)
+    e_c = 2^(k_c * h'/R' + b_c)             MUFU.EX2 (<= 2 ulp), float32 sums, float32 optical depth
+with R' = R - R/4096.  This test replays exactly that arithmetic on the CPU (float32 numpy, FMA emulated through
+float64) for random rays of the shipped atmosphere and compares the transmittance with the float64 reference
+formula h = |q| - R.  It pins the precision claims without a GPU: the cancellation-free form keeps the error of
+exp(-tau) below 1e-5 even at optical depth 20+, where naive float32 `|q| - R` is off by more than 1e-3.
+"""
+import numpy as np
+
+R = 6378000.0
+HEIGHT = 35000.0
+SCALE = (1200.0, 8000.0)                               # mie, rayleigh
+EXT = (np.array([2e-5 / 0.9] * 3), np.array([5.8e-6, 13.5e-6, 33.1e-6]))
+STEPS = 100
+LOG2E = 1.4426950408889634
+
+f32 = np.float32
+
+
+def fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+
+def trunc_to_f32(x):
+    """float image of a positive double by truncation (device: IADD + SHF on the double's words)."""
+    y = x.astype(f32)
+    too_big = y.astype(np.float64) > x
+    return np.where(too_big, np.nextafter(y, f32(0)), y).astype(f32)
+
+
+def ray_samples(rng, n):
+    """Random (start radius, sine of elevation) pairs whose ray to the top of the atmosphere stays above ground."""
+    r0 = R + rng.uniform(0.0, HEIGHT, n)
+    horizon = -np.sqrt(np.maximum(0.0, 1.0 - (R / r0) ** 2))
+    mu = rng.uniform(horizon + 1e-6, 1.0, n)
+    rt = R + HEIGHT
+    t_end = -r0 * mu + np.sqrt((r0 * mu) ** 2 - (r0 ** 2 - rt ** 2))      # distance to the shell
+    return r0, mu, t_end
+
+
+def column_reference(r0, mu, t_end):
+    m = (np.arange(STEPS) + 0.5)[None, :]
+    t = t_end[:, None] * m / STEPS
+    rq = np.sqrt(r0[:, None] ** 2 + 2 * t * r0[:, None] * mu[:, None] + t ** 2)
+    h = rq - R
+    seg = t_end / STEPS
+    return [np.exp(-h / s).sum(axis=1) * seg for s in SCALE]
+
+
+def column_kernel_model(r0, mu, t_end):
+    delta = R / 4096.0
+    rp = R - delta
+    inv_rp2 = 1.0 / (rp * rp)
+    a = (r0 ** 2 - rp * rp) * inv_rp2
+    b = (2.0 * r0 * mu * t_end / STEPS) * inv_rp2
+    c = (t_end ** 2 / STEPS ** 2) * inv_rp2
+    m = (np.arange(STEPS) + 0.5)[None, :]
+    u = a[:, None] + m * (b[:, None] + m * c[:, None])                    # float64, as the device's DADD chain
+    uf = trunc_to_f32(u)
+    q = fma32(uf, np.full_like(uf, f32(0.02734375)), np.full_like(uf, f32(-0.0390625)))
+    q = fma32(q, uf, np.full_like(uf, f32(0.0625)))
+    q = fma32(q, uf, np.full_like(uf, f32(-0.125)))
+    q = fma32(q, uf, np.full_like(uf, f32(0.5)))
+    hq = (uf * q).astype(f32)
+    cols = []
+    for s in SCALE:
+        k = f32(-rp * LOG2E / s)
+        bb = f32(delta * LOG2E / s)
+        arg = fma32(hq, np.full_like(hq, k), np.full_like(hq, bb))
+        e = np.exp2(arg.astype(np.float64)).astype(f32)                   # MUFU.EX2 is within 2 ulp of this
+        acc = np.zeros(len(r0), dtype=f32)
+        for j in range(STEPS):                                            # float32 running sum, like the device
+            acc = (acc + e[:, j]).astype(f32)
+        seg = (t_end / STEPS).astype(f32)
+        cols.append((acc * seg).astype(f32).astype(np.float64))
+    return cols
+
+
+def column_naive_f32(r0, mu, t_end):
+    m = (np.arange(STEPS) + 0.5)[None, :].astype(f32)
+    t = ((t_end[:, None] / STEPS).astype(f32) * m).astype(f32)
+    r0f, muf = r0.astype(f32)[:, None], mu.astype(f32)[:, None]
+    rq = np.sqrt((r0f * r0f + f32(2) * t * r0f * muf + t * t).astype(f32)).astype(f32)
+    h = (rq - f32(R)).astype(f32)
+    seg = (t_end / STEPS).astype(f32)
+    return [(np.exp(-(h / f32(s)).astype(f32)).astype(f32).sum(axis=1, dtype=f32) * seg).astype(np.float64)
+            for s in SCALE]
+
+
+def transmittance(cols):
+    tau = cols[0][:, None] * EXT[0][None, :] + cols[1][:, None] * EXT[1][None, :]
+    return np.exp(-tau), tau
+
+
+def test_kernel_sampler_model_meets_the_tolerance():
+    rng = np.random.default_rng(42)
+    r0, mu, t_end = ray_samples(rng, 4000)
+    ref, tau = transmittance(column_reference(r0, mu, t_end))
+    got, _ = transmittance(column_kernel_model(r0, mu, t_end))
+    err = np.abs(got - ref) / ref
+    assert tau.max() > 15.0                                   # the sample reaches the deep-twilight regime
+    assert err.max() < 1e-5                                   # ten times inside the 1e-4 tolerance
+    assert np.median(err) < 2e-7
+
+
+def test_naive_float32_height_fails_the_tolerance():
+    """Why the cancellation-free form is needed (naive FP32 |p| - R gives 1.8e-3)."""
+    rng = np.random.default_rng(42)
+    r0, mu, t_end = ray_samples(rng, 4000)
+    ref, _ = transmittance(column_reference(r0, mu, t_end))
+    naive, _ = transmittance(column_naive_f32(r0, mu, t_end))
+    assert (np.abs(naive - ref) / ref).max() > 1e-4
+
+
+def test_height_series_is_accurate_over_its_whole_range():
+    """sqrt(1+u) - 1 through the degree-4 series for u up to 0.05 (the threshold of the fast path)."""
+    u = np.linspace(1e-4, 0.05, 20001)
+    series = u * (0.5 - u / 8 + u ** 2 / 16 - 5 * u ** 3 / 128 + 7 * u ** 4 / 256)
+    exact = np.sqrt(1 + u) - 1
+    assert np.max(np.abs(series - exact) / exact) < 2e-8
