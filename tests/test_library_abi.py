@@ -168,3 +168,23 @@ def test_product_package_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_hot_kernel_uses_blackwell_packed_fp32_and_mufu():
+    """SASS of the built library: the first-order kernel's sampler runs on FFMA2/FMUL2/FADD2 (sm_100 packed FP32),
+    MUFU.EX2 and DADD, and the library is compiled for sm_100a only."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "libsfsim_atmosphere.so")
+    arch = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in arch and "sm_90" not in arch and "sm_80" not in arch
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True).stdout
+    start = sass.index("k_first_order")
+    end = sass.find("Function :", start + 1)
+    body = sass[start:end if end > 0 else len(sass)]
+    for mnemonic in ("FFMA2", "FMUL2", "FADD2", "MUFU.EX2", "DADD"):
+        assert mnemonic in body, mnemonic
+    assert body.count("MUFU.EX2") >= 8
