@@ -489,17 +489,48 @@ typedef struct {
   const double *x, *v, *l;
 } ps_ctx;
 
+/* Test hooks: the analogue of the reference tests' with-redefs (t_atmosphere.clj:330-361 rebinds atmosphere/phase,
+ * atmosphere/ray-extremity and atmosphere/transmittance around point-scatter).  NULL = the real function.  Only the
+ * point-scatter integrand consults them, and only the known-answer tests set them. */
+static orc_test_hooks g_hooks = {0, 0, 0};
+
+void orc_set_test_hooks(const orc_test_hooks *hooks) {
+  if (hooks)
+    g_hooks = *hooks;
+  else
+    memset(&g_hooks, 0, sizeof g_hooks);
+}
+
 static void in_scatter_from_direction(void *vctx, const double omega[3], double *out) {
   ps_ctx *c = (ps_ctx *)vctx;
   double point[3], overall[3], rs[3], extra[3] = {0, 0, 0};
-  orc_ray_extremity(c->planet, c->x, omega, point);
+  if (g_hooks.ray_extremity)
+    g_hooks.ray_extremity(c->planet, c->x, omega, point);
+  else
+    orc_ray_extremity(c->planet, c->x, omega, point);
   int surface = orc_surface_point(c->planet, point);
-  overall_in_scattering(c->planet, c->scatter, c->n, c->x, c->v, omega, overall);
+  if (g_hooks.phase) {
+    /* overall-in-scattering (atmosphere.clj:147-151) with the rebound phase */
+    for (int i = 0; i < c->n; i++) {
+      double s[3];
+      orc_scattering(&c->scatter[i], orc_height(c->planet, c->x), s);
+      double ph = g_hooks.phase(&c->scatter[i], dot3(c->v, omega));
+      for (int k = 0; k < 3; k++) {
+        double term = s[k] * ph;
+        overall[k] = (i == 0) ? term : overall[k] + term;
+      }
+    }
+  } else {
+    overall_in_scattering(c->planet, c->scatter, c->n, c->x, c->v, omega, overall);
+  }
   c->ray_scatter(c->rs_ctx, c->x, omega, c->l, !surface, rs);
   if (surface) {
     double e[3], t[3];
     c->surface_radiance(c->sr_ctx, point, c->l, e);
-    orc_transmittance(c->planet, c->scatter, c->n, c->ray_steps, c->x, point, t);
+    if (g_hooks.transmittance)
+      g_hooks.transmittance(c->planet, c->scatter, c->n, c->ray_steps, c->x, point, t);
+    else
+      orc_transmittance(c->planet, c->scatter, c->n, c->ray_steps, c->x, point, t);
     for (int i = 0; i < 3; i++) {
       double surface_brightness = (c->planet->brightness[i] / M_PI) * e[i];
       extra[i] = t[i] * surface_brightness;
@@ -520,6 +551,16 @@ void orc_point_scatter(const orc_planet *planet, const orc_scatter *scatter, int
   normalize3(d, normal);
   ps_ctx c = {planet, scatter, n, ray_scatter, rsc, surface_radiance, src, ray_steps, x, v, l};
   orc_integral_sphere(sphere_steps, normal, in_scatter_from_direction, &c, 3, out);
+}
+
+/* the integrand of point-scatter for ONE direction omega (the `fun` the reference hands to integral-sphere,
+ * atmosphere.clj:208-222): what t_atmosphere.clj:330-361 probes through its integral-sphere mock */
+void orc_in_scatter_from_direction(const orc_planet *planet, const orc_scatter *scatter, int n,
+                                   orc_point_fn ray_scatter, void *rsc, orc_surface_fn surface_radiance, void *src,
+                                   long ray_steps, const double x[3], const double v[3], const double l[3],
+                                   const double omega[3], double out[3]) {
+  ps_ctx c = {planet, scatter, n, ray_scatter, rsc, surface_radiance, src, ray_steps, x, v, l};
+  in_scatter_from_direction(&c, omega, out);
 }
 
 typedef struct {
@@ -1056,5 +1097,32 @@ void orc_roundtrip_e(const orc_planet *planet, const orc_config *cfg, double *ou
     unravel(i, cfg->shape_e, 2, idx);
     orc_surface_radiance_backward(planet, cfg->shape_e, idx[0], idx[1], x, l);
     orc_surface_radiance_forward(planet, cfg->shape_e, x, l, out + 2 * i);
+  }
+}
+
+/* backward(i) of every integer texel of the three spaces (atmosphere.clj:302-310, 348-356, 401-412): the inputs each
+ * table entry is integrated for.  Used by the full-grid index-map parity test.  Unused outputs may be NULL. */
+void orc_backward_all(const orc_planet *planet, const orc_config *cfg, int which, double *point, double *direction,
+                      double *light, int *above) {
+  const long *shape = which == 0 ? cfg->shape4 : which == 1 ? cfg->shape_e : cfg->shape_t;
+  const int dims = which == 0 ? 4 : 2;
+  long count = prod(shape, dims);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < count; i++) {
+    double idx[4], x[3], v[3] = {0, 0, 0}, l[3] = {0, 0, 0};
+    int ab = 0;
+    unravel(i, shape, dims, idx);
+    if (which == 0)
+      orc_ray_scatter_backward(planet, shape, idx[0], idx[1], idx[2], idx[3], x, v, l, &ab);
+    else if (which == 1)
+      orc_surface_radiance_backward(planet, shape, idx[0], idx[1], x, l);
+    else
+      orc_transmittance_backward(planet, shape, idx[0], idx[1], x, v, &ab);
+    for (int c = 0; c < 3; c++) {
+      if (point) point[3 * i + c] = x[c];
+      if (direction) direction[3 * i + c] = v[c];
+      if (light) light[3 * i + c] = l[c];
+    }
+    if (above) above[i] = ab;
   }
 }

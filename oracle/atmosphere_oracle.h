@@ -100,6 +100,18 @@ void orc_point_scatter(const orc_planet *planet, const orc_scatter *scatter, int
                        void *rs_ctx, orc_surface_fn surface_radiance, void *sr_ctx, const double intensity[3],
                        long sphere_steps, long ray_steps, const double x[3], const double v[3], const double l[3],
                        int above, double out[3]);
+/* test hooks (with-redefs analogue) and the single-direction integrand of point-scatter */
+typedef struct {
+  double (*phase)(const orc_scatter *s, double mu);
+  void (*ray_extremity)(const orc_planet *planet, const double origin[3], const double direction[3], double out[3]);
+  void (*transmittance)(const orc_planet *planet, const orc_scatter *scatter, int n, long steps, const double x[3],
+                        const double x0[3], double out[3]);
+} orc_test_hooks;
+void orc_set_test_hooks(const orc_test_hooks *hooks);
+void orc_in_scatter_from_direction(const orc_planet *planet, const orc_scatter *scatter, int n,
+                                   orc_point_fn ray_scatter, void *rs_ctx, orc_surface_fn surface_radiance,
+                                   void *sr_ctx, long ray_steps, const double x[3], const double v[3],
+                                   const double l[3], const double omega[3], double out[3]);
 void orc_surface_radiance(const orc_planet *planet, orc_point_fn ray_scatter, void *rs_ctx, long steps,
                           const double x[3], const double l[3], double out[3]);
 
@@ -181,6 +193,9 @@ void orc_table_resample_sum_t(const orc_planet *planet, const orc_config *cfg, c
 void orc_roundtrip_4d(const orc_planet *planet, const orc_config *cfg, double *out);
 void orc_roundtrip_t(const orc_planet *planet, const orc_config *cfg, double *out);
 void orc_roundtrip_e(const orc_planet *planet, const orc_config *cfg, double *out);
+/* backward(i) for every integer texel; which: 0 = ray-scatter-space, 1 = surface-radiance-space, 2 = transmittance-space */
+void orc_backward_all(const orc_planet *planet, const orc_config *cfg, int which, double *point, double *direction,
+                      double *light, int *above);
 
 /* counters: overall-extinction evaluations ("E-samples") and table lookups since the last reset */
 void orc_counters_reset(void);

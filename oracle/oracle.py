@@ -330,6 +330,56 @@ def point_scatter(pl, scatters, ray_scatter_fn, surface_radiance_fn, intensity, 
     return _np3(out)
 
 
+PHASE_HOOK = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double)
+EXTREMITY_HOOK = C.CFUNCTYPE(None, C.c_void_p, c_double_p, c_double_p, c_double_p)
+TRANSMITTANCE_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_long, c_double_p, c_double_p, c_double_p)
+
+
+class TestHooks(C.Structure):
+    _fields_ = [("phase", PHASE_HOOK), ("ray_extremity", EXTREMITY_HOOK), ("transmittance", TRANSMITTANCE_HOOK)]
+
+
+class redefs:
+    """Context manager: the oracle's analogue of the reference tests' with-redefs around point-scatter
+    (t_atmosphere.clj:330-361).  phase(mu) -> float, ray_extremity(origin, direction) -> vec3,
+    transmittance(steps, x, x0) -> vec3; None keeps the real function."""
+
+    def __init__(self, phase=None, ray_extremity=None, transmittance=None):
+        def ph(_s, mu):
+            return float(phase(mu))
+
+        def ext(_pl, o, d, out):
+            val = ray_extremity(np.array([o[0], o[1], o[2]]), np.array([d[0], d[1], d[2]]))
+            for i in range(3):
+                out[i] = float(val[i])
+
+        def tr(_pl, _sc, _n, steps, x, x0, out):
+            val = transmittance(int(steps), np.array([x[0], x[1], x[2]]), np.array([x0[0], x0[1], x0[2]]))
+            for i in range(3):
+                out[i] = float(val[i])
+
+        self.hooks = TestHooks(PHASE_HOOK(ph) if phase else PHASE_HOOK(),
+                               EXTREMITY_HOOK(ext) if ray_extremity else EXTREMITY_HOOK(),
+                               TRANSMITTANCE_HOOK(tr) if transmittance else TRANSMITTANCE_HOOK())
+
+    def __enter__(self):
+        lib().orc_set_test_hooks(C.byref(self.hooks))
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_test_hooks(None)
+        return False
+
+
+def in_scatter_from_direction(pl, scatters, ray_scatter_fn, surface_radiance_fn, ray_steps, x, v, l, omega):
+    """The integrand point-scatter hands to integral-sphere, for one direction (atmosphere.clj:208-222)."""
+    out = _out3()
+    lib().orc_in_scatter_from_direction(C.byref(pl), scatter_array(scatters), len(scatters), _point_cb(ray_scatter_fn),
+                                        None, _surface_cb(surface_radiance_fn), None, C.c_long(ray_steps), vec3(x),
+                                        vec3(v), vec3(l), vec3(omega), out)
+    return _np3(out)
+
+
 def surface_radiance(pl, ray_scatter_fn, steps, x, l):
     out = _out3()
     lib().orc_surface_radiance(C.byref(pl), _point_cb(ray_scatter_fn), None, C.c_long(steps), vec3(x), vec3(l), out)
@@ -585,6 +635,18 @@ def roundtrip(pl, cfg, which):
     fn = {0: "orc_roundtrip_4d", 1: "orc_roundtrip_e", 2: "orc_roundtrip_t"}[which]
     getattr(lib(), fn)(C.byref(pl), C.byref(cfg), _tab_ptr(out))
     return out
+
+
+def backward_all(pl, cfg, which):
+    """backward(i) of every integer texel of ray-scatter-space (which=0), surface-radiance-space (1) or
+    transmittance-space (2): (point, direction, light, above) arrays in row-major texel order."""
+    shape = {0: tuple(cfg.shape4), 1: tuple(cfg.shape_e), 2: tuple(cfg.shape_t)}[which]
+    n = int(np.prod(shape))
+    p, d, l = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    ab = np.zeros(n, dtype=np.int32)
+    lib().orc_backward_all(C.byref(pl), C.byref(cfg), C.c_int(which), _tab_ptr(p), _tab_ptr(d), _tab_ptr(l),
+                           ab.ctypes.data_as(C.POINTER(C.c_int)))
+    return p, d, l, ab.astype(bool)
 
 
 def counters_reset():

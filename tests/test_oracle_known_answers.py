@@ -189,6 +189,70 @@ def test_point_scatter_direction_integrand():
         assert above == (not orc.surface_point(earth, orc.ray_extremity(earth, x2, view)))
 
 
+def test_point_scatter_integrand_reference_values():
+    """The numeric facts of t_atmosphere.clj:304-361, with the same rebindings (orc.redefs = with-redefs):
+    phase -> 0.5, ray-extremity and transmittance mocked, integral-sphere replaced by probing the integrand at
+    one direction.  Expected values are the reference's literals, not recomputed from the oracle."""
+    radius, height = 6378000.0, 100000.0
+    x1 = np.array([0.0, radius, 0.0])
+    x2 = np.array([0.0, radius + 1200.0, 0.0])
+    light = np.array([0.36, 0.48, 0.8])
+    earth = orc.planet(radius, height, brightness=tuple(0.3 * PI for _ in range(3)))
+    mie = orc.scatter((2e-5,) * 3, 1200.0, g=0.76)
+    seen = {}
+
+    def ray_scatter1(x, view, l, above):
+        np.testing.assert_array_equal(x, x1)
+        np.testing.assert_array_equal(view, (0, 1, 0))
+        np.testing.assert_array_equal(l, light)
+        assert above is True
+        return (1, 2, 3)
+
+    def ray_scatter2(x, view, l, above):
+        np.testing.assert_array_equal(x, x2)
+        np.testing.assert_array_equal(view, (0, -1, 0))
+        np.testing.assert_array_equal(l, light)
+        assert above is False
+        return (0, 0, 0)
+
+    def surface_radiance(x, l):
+        seen["surface_radiance_point"] = x.copy()
+        np.testing.assert_array_equal(l, light)
+        return (3, 4, 5)
+
+    # case 1 (t_atmosphere.clj:331-340): the ray leaves the atmosphere
+    with orc.redefs(phase=lambda mu: 0.5, ray_extremity=lambda o, d: (0, radius + height, 0)):
+        got = orc.in_scatter_from_direction(earth, [mie], ray_scatter1, surface_radiance, 10, x1, (0, 1, 0), light,
+                                            (0, 1, 0))
+    np.testing.assert_allclose(got, np.array([1, 2, 3]) * 2e-5 * 0.5, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got, np.array([1e-5, 2e-5, 3e-5]), rtol=1e-12)
+
+    # case 2 (t_atmosphere.clj:341-361): the ray hits the ground
+    def extremity(o, d):
+        np.testing.assert_array_equal(o, x2)
+        np.testing.assert_array_equal(d, (0, -1, 0))
+        return (0, radius, 0)
+
+    def transmittance(steps, x, x0):
+        assert steps == 10
+        np.testing.assert_array_equal(x, x2)
+        np.testing.assert_array_equal(x0, (0, radius, 0))
+        return (0.9, 0.8, 0.7)
+
+    with orc.redefs(phase=lambda mu: 0.5, ray_extremity=extremity, transmittance=transmittance):
+        got = orc.in_scatter_from_direction(earth, [mie], ray_scatter2, surface_radiance, 10, x2, (0, 1, 0), light,
+                                            (0, -1, 0))
+    want = np.array([0.9, 0.8, 0.7]) * np.array([3.0, 4.0, 5.0]) * (0.5 * (2e-5 / math.e) * 0.3)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    np.testing.assert_array_equal(seen["surface_radiance_point"], (0, radius, 0))
+    # the hooks are gone afterwards: the real phase function is back (t_atmosphere.clj phase facts)
+    with orc.redefs():
+        pass
+    got = orc.in_scatter_from_direction(earth, [mie], ray_scatter1, surface_radiance, 10, x1, (0, 1, 0), light, (0, 1, 0))
+    np.testing.assert_allclose(got, np.array([1, 2, 3]) * 2e-5 * orc.phase(mie, 1.0), rtol=1e-12)
+
+
 # ---------------------------------------------------------------- t_atmosphere.clj:364-383 (E(S))
 
 def test_surface_radiance_integrand():
