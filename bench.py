@@ -10,14 +10,20 @@ point-scatter / surface-radiance / ray-scatter / accumulation, and the final res
 Inputs are parameters only (deterministic, no data files), so "inputs resident in HBM" means the builder
 with its quadrature tables and table buffers exists before the timed region.
 
-metric = ray-scatter texels per second = 4-D texels x (1 + iterations) scattering orders / build time.
-With N > 1 (torchrun, one process per GPU) the SAME build is sharded over the ranks (strong scaling): each
-rank integrates a contiguous slab of (height, elevation) pairs of every 4-D table and the tables are
-reassembled by one NCCL all-gather each (12 per build).
+metric (`value`) = 4-D texels x (1 + iterations) scattering orders / build time: the build rate, strong scaling.
+The per-kernel rates SURVEY.md 8(d) names are printed beside it: `ray_scatter_pass_texels_per_s` = N4 / (one
+ray-scatter pass) and `first_order_texels_per_s` = N4 / (the first-order pass).
 
-`--impl reference` times the reference algorithm on the host cores: the double-precision CPU oracle
-(oracle/, a restatement of the Clojure code -- there is no JVM on the box) on a bounded random sample of
-texels of every stage, extrapolated per texel to the full build.
+With N > 1 (torchrun, one process per GPU) the SAME build is sharded over the ranks.  Default exchange `p2p`: whole
+height rows are dealt to the ranks, the kernels store every finished texel into all GPUs' tables over NVLink (CUDA
+IPC) and a flag barrier closes each table -- no collective moves table data.  `--mode nccl`: contiguous slabs and
+one NCCL all-gather per table (12 per build); its build time is also measured and printed as `nccl_mode` in the
+default run.  Outside the timed region rank 0 builds the same tables on one GPU and compares the sharded result byte
+for byte (`sharded_identical`, both modes); a difference makes the run fail.
+
+`--impl reference` times the reference algorithm on the host cores: the double-precision CPU oracle (oracle/, a
+restatement of the Clojure code -- there is no JVM on the box) on a bounded random sample of texels of every stage,
+extrapolated per texel to the full build, on ALL host cores (also under torchrun, which exports OMP_NUM_THREADS=1).
 """
 import argparse
 import ctypes
@@ -35,6 +41,8 @@ METRIC = "ray_scatter_texels_per_s"
 UNIT = "texels/s"
 WORKLOAD = "full atmosphere-lut build, shipped resolution (4-D 32x127x32x8, T 64x255, E 16x63, ray-steps 100, " \
            "sphere-steps 15, 5 iterations), Earth defaults"
+STRESS_WORKLOAD = "stress: 4-D 64x253x64x16 (2x shipped per axis), T 64x255, E 16x63, ray-steps 100, sphere-steps 15, " \
+                  "10 iterations, Earth defaults"
 
 
 def parse():
@@ -51,6 +59,8 @@ def parse():
                     help="shipped = BASELINE.json configs[2] (the headline); stress = configs[4]: 4-D table at 2x "
                          "resolution per axis (64x253x64x16), 10 iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the stress build, the other exchange mode and the identity checks (profiling runs)")
     return ap.parse_args()
 
 
@@ -106,11 +116,11 @@ class ClockSampler:
 # ------------------------------------------------------------------ CPU baseline (oracle; checker only)
 
 def cpu_baseline(sample, threads=None):
-    """Times the CPU oracle on `sample` random texels of every stage and extrapolates to the full build."""
+    """Times the CPU oracle on `sample` random texels of every stage and extrapolates to the full build.
+    All host cores by default: torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly."""
     import numpy as np
     from oracle import oracle as orc
-    if threads:
-        orc.set_num_threads(threads)
+    orc.set_num_threads(threads or os.cpu_count() or 1)
     cores = orc.num_threads()
     pl = orc.planet(**orc.EARTH)
     mie, ray = orc.scatter(**orc.MIE), orc.scatter(**orc.RAYLEIGH)
@@ -157,7 +167,8 @@ def cpu_baseline(sample, threads=None):
                       "tables synthetic; extrapolated per texel to the full build" % (len(idx4), len(idxe)),
             "sample_cpu_s": sample_s, "build_time_s_extrapolated": full_s, "extrapolated": True,
             "esamples_in_sample": counters["esamples"],
-            "note": "CPU restatement in C (double, OpenMP), not JVM Clojure: a lower bound on the reference's time",
+            "note": "CPU restatement in C (double, OpenMP), not JVM Clojure: a lower bound on the reference's time; "
+                    "the same oracle ran the WHOLE shipped build in 755 s on 8 cores (tests/golden/make_shipped_golden.py)",
             "stages": {k: round(v["full_s"], 3) for k, v in stages.items()}}
 
 
@@ -192,6 +203,53 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ B200 arm
 
+def stage_sums(stage_times):
+    """[(name, ms)] -> {key: ms} with the per-iteration stages summed ("iter3_ray_scatter" -> "ray_scatter")."""
+    out = {}
+    for name, ms in stage_times:
+        key = name.split("_", 1)[1] if name.startswith("iter") else name
+        out[key] = out.get(key, 0.0) + ms
+    return out
+
+
+class Runner:
+    """One configuration on this rank's GPU: device-timed steps of builder.run()."""
+
+    def __init__(self, torch, dist, world, flush):
+        self.torch, self.dist, self.world, self.flush = torch, dist, world, flush
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def time_steps(self, builder, steps, warmup):
+        """(ms per step, max over ranks): CUDA events on the builder's stream around every build, a 512 MiB
+        write between steps so that no table survives in L2."""
+        torch = self.torch
+        stream = torch.cuda.ExternalStream(builder.stream)
+        for _ in range(max(warmup, 3)):
+            builder.run()
+        self.barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            with torch.cuda.stream(stream):
+                self.flush.zero_()                      # evict the previous step's tables from L2
+            starts[i].record(stream)
+            builder.run()
+            ends[i].record(stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        builder.sync()                                  # surfaces a barrier timeout as an error
+        total = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(total, op=self.dist.ReduceOp.MAX)
+        return float(total.item()) / steps, wall
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -210,163 +268,246 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
     _lib.check(lib.atmlut_init(local_rank))
-    cfg = _lib.default_config()
-    workload = WORKLOAD
-    if args.workload == "stress":
-        cfg = _lib.make_config(ray_scatter_shape=(64, 253, 64, 16), iterations=10)
-        workload = "stress: 4-D 64x253x64x16 (2x shipped per axis), T 64x255, E 16x63, ray-steps 100, sphere-steps 15, " \
-                   "10 iterations, Earth defaults"
-    builder = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world, mode=args.mode)
-    stream = torch.cuda.ExternalStream(lib.atmlut_stream())
+    shipped_cfg = _lib.default_config()
+    stress_cfg = _lib.make_config(ray_scatter_shape=(64, 253, 64, 16), iterations=10)
+    cfg, workload = (shipped_cfg, WORKLOAD) if args.workload == "shipped" else (stress_cfg, STRESS_WORKLOAD)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    runner = Runner(torch, dist, world, flush)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def texels_of(c):
+        return c.height_size * c.elevation_size * c.light_elevation_size * c.heading_size
 
-    def step_device():
-        builder.run()
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
+    # ---------------- the headline: device-timed builds
+    builder = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world, mode=args.mode)
     sampler = ClockSampler(local_rank)
+    runner.time_steps(builder, 2, args.warmup)          # warm-up (graph capture, clocks)
     sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()                      # evict the previous step's tables from L2
-        starts[i].record(stream)
-        step_device()
-        ends[i].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    ms_per_step, t_wall = runner.time_steps(builder, args.steps, 0)
     clocks = sampler.stop()
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    ms_per_step = total_ms / args.steps
-    stage_times = builder.stage_times()
     work = builder.work()
-    # per-rank stage times (the barrier / all-gather stages absorb the load imbalance between ranks)
-    my_stages = {}
-    for name, ms in stage_times:
-        key = name.split("_", 1)[1] if name.startswith("iter") else name
-        my_stages[key] = my_stages.get(key, 0.0) + ms
+
+    # ---------------- per-stage times: the same build launched kernel by kernel with events
+    builder.run_timed()
+    builder.sync()
+    runner.barrier()
+    builder.run_timed()
+    builder.sync()
+    stage_times = builder.stage_times()
+    my_stages = stage_sums(stage_times)
     all_stages = [my_stages]
     if world > 1:
         all_stages = [None] * world
         dist.all_gather_object(all_stages, my_stages)
 
-    # end to end through the public one-shot call: host parameters in, host (pinned) tables out
-    e2e = None
+    n4 = texels_of(cfg)
+    texels = n4 * (1 + cfg.iterations)
+    d2h = sum(int(np.prod(s)) * 4 for s in atmosphere_lut.output_shapes(cfg))
+    h2d = ctypes.sizeof(_lib.Planet) + 2 * ctypes.sizeof(_lib.Scatter) + ctypes.sizeof(_lib.Config)
+
+    # ---------------- end to end through the public call: host parameters in, host tables out
+    def time_e2e(fn, n):
+        runner.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        runner.barrier()
+        return (time.perf_counter() - t0) / n
+
+    n_e2e = max(5, args.steps // 3)
+    e2e_pageable = None
     if world == 1:
         out = atmosphere_lut.allocate_outputs(cfg, pinned=True)
         for _ in range(3):
             atmosphere_lut.generate_tables(cfg=cfg, out=out)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = max(5, args.steps // 3)
-        for _ in range(n_e2e):
-            atmosphere_lut.generate_tables(cfg=cfg, out=out)
-        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_s = time_e2e(lambda: atmosphere_lut.generate_tables(cfg=cfg, out=out), n_e2e)
+        # what a host without pinned buffers gets (the JVM's FFM arenas): pageable destinations, staged by the library
+        out_p = atmosphere_lut.allocate_outputs(cfg, pinned=False)
+        for o in out_p:
+            o.fill(0)                                   # touch the pages once, like a reused arena
+        atmosphere_lut.generate_tables(cfg=cfg, out=out_p)
+        e2e_pageable_s = time_e2e(lambda: atmosphere_lut.generate_tables(cfg=cfg, out=out_p), n_e2e)
+        e2e_pageable = {"value": texels / e2e_pageable_s, "unit": UNIT, "build_time_s": e2e_pageable_s,
+                        "note": "atmlut_generate into pageable host memory (malloc / JVM arena): the download is "
+                                "pipelined through two library-owned pinned buffers"}
+        api = "atmlut_generate"
     else:
-        # sharded: device build + download of the file-layout tables on rank 0
         out = atmosphere_lut.allocate_outputs(cfg, pinned=True)
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(5, args.steps // 3)
-        for _ in range(n_e2e):
+
+        def sharded_e2e():
             builder.run()
             if rank == 0:
                 builder.download(out)
             else:
                 builder.sync()
-            if world > 1:
-                dist.barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-    n4 = cfg.height_size * cfg.elevation_size * cfg.light_elevation_size * cfg.heading_size
-    texels = n4 * (1 + cfg.iterations)
-    d2h = sum(int(np.prod(s)) * 4 for s in atmosphere_lut.output_shapes(cfg))
-    h2d = ctypes.sizeof(_lib.Planet) + 2 * ctypes.sizeof(_lib.Scatter) + ctypes.sizeof(_lib.Config)
+        sharded_e2e()
+        e2e_s = time_e2e(sharded_e2e, n_e2e)
+        api = "atmlut_builder_run + atmlut_builder_download on rank 0"
     e2e = {"value": texels / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "build_time_s": e2e_s, "api": "atmlut_generate" if world == 1 else "atmlut_builder_run+download"}
+           "build_time_s": e2e_s, "api": api, "host_buffers": "pinned"}
 
-    # roofline of the dominant E-sample kernel (first-order ray scatter): MUFU.EX2 pipe
+    # ---------------- identity of the sharded build, the other exchange mode, the stress configuration
+    extras = {}
+    identical = None
+    if not args.no_extras:
+        def single_gpu_tables(c):
+            if rank != 0:
+                return None
+            single = atmosphere_lut.AtmosphereLutBuilder(cfg=c)
+            single.run()
+            single.sync()
+            t = single.download()
+            single.close()
+            return t
+
+        def same_bytes(b, want):
+            flag = torch.zeros(1, device="cuda")
+            if rank == 0:
+                got = b.download()
+                flag[0] = 1.0 if all(np.array_equal(g, w) for g, w in zip(got, want)) else 0.0
+            if world > 1:
+                dist.broadcast(flag, 0)
+            return bool(flag.item() > 0.5)
+
+        if world > 1:
+            want = single_gpu_tables(cfg)
+            builder.run()
+            builder.sync()
+            runner.barrier()
+            identical = {args.mode: same_bytes(builder, want)}
+            other = "nccl" if args.mode == "p2p" else "p2p"
+            b2 = atmosphere_lut.AtmosphereLutBuilder(cfg=cfg, rank=rank, world=world, mode=other)
+            ms2, _ = runner.time_steps(b2, max(3, args.steps // 2), 3)
+            identical[other] = same_bytes(b2, want)
+            extras["%s_mode" % other] = {"ms_per_step": ms2, "value": texels / (ms2 * 1e-3), "unit": UNIT,
+                                         "note": "the same sharded build with the other exchange"}
+            if other == "nccl":
+                extras["nccl_mode"]["all_gathers_per_build"] = b2.gathers // (max(3, args.steps // 2) + 3)
+            b2.close()
+        if args.workload == "shipped":
+            # BASELINE.json configs[4] beside the headline
+            sb = atmosphere_lut.AtmosphereLutBuilder(cfg=stress_cfg, rank=rank, world=world, mode=args.mode)
+            s_ms, _ = runner.time_steps(sb, 3, 2)
+            sb.run_timed()
+            sb.sync()
+            runner.barrier()
+            sb.run_timed()
+            sb.sync()
+            s_stages = stage_sums(sb.stage_times())
+            s_n4 = texels_of(stress_cfg)
+            extras["stress"] = {"workload": STRESS_WORKLOAD, "ms_per_step": s_ms,
+                                "value": s_n4 * (1 + stress_cfg.iterations) / (s_ms * 1e-3), "unit": UNIT,
+                                "stage_ms_rank0": {k: round(v, 3) for k, v in s_stages.items()}, "steps": 3}
+            if world > 1:
+                s_want = single_gpu_tables(stress_cfg)
+                sb.run()
+                sb.sync()
+                runner.barrier()
+                extras["stress"]["sharded_identical"] = same_bytes(sb, s_want)
+                if identical is not None:
+                    identical["stress_" + args.mode] = extras["stress"]["sharded_identical"]
+            sb.close()
+
+    # ---------------- rooflines
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks_b200.json")))
     except Exception:
         pass
-    first_ms = dict(stage_times).get("first_order")
-    esamples_first = None
-    roofline = None
-    if first_ms:
-        # E-samples of this rank's first-order launch: counter 0 of the builder (exact, counted on the device)
-        esamples_first = work.get("esamples_first_order")
+    first_ms = my_stages.get("first_order")
+    ray_ms = my_stages.get("ray_scatter")
+    point_ms = my_stages.get("point_scatter")
     if rank == 0:
-        stage_dict = {}
-        for name, ms in stage_times:
-            key = name.split("_", 1)[1] if name.startswith("iter") else name
-            stage_dict[key] = stage_dict.get(key, 0.0) + ms
         launches_per_step = int(work["kernel_launches"])
         mufu_peak = peaks.get("mufu_ex2_per_s")
-        # DRAM traffic of one K3 launch from the committed `ncu --set full` capture, and the driver-measured HBM peak
-        traffic = None
-        try:
-            text = open(os.path.join(ROOT, "profiles", "r1_final_ncu_summary.txt")).read().split("== k_point_scatter")[0]
-            units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            traffic = 0.0
-            for line in text.splitlines():
-                if "dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line:
-                    parts = line.split()
-                    traffic += float(parts[1]) * units[parts[2]]
-        except Exception:
-            traffic = None
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clock_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
+        # DRAM traffic of one first-order launch from the committed `ncu --set full` capture (single GPU only)
+        traffic, traffic_source = None, None
+        if world == 1 and args.workload == "shipped":
+            for name in ("r2_ncu_summary.txt", "r1_final_ncu_summary.txt"):
+                try:
+                    text = open(os.path.join(ROOT, "profiles", name)).read().split("== k_point_scatter")[0]
+                    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    traffic = 0.0
+                    for ln in text.splitlines():
+                        if "dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln:
+                            parts = ln.split()
+                            traffic += float(parts[1]) * units[parts[2]]
+                    traffic_source = "from_profile: profiles/%s (one ncu --set full capture of this kernel, not this run)" % name
+                    break
+                except Exception:
+                    traffic = None
+        roofline = None
         if first_ms and work.get("esamples_first_order") and mufu_peak:
             achieved = 2.0 * work["esamples_first_order"] / (first_ms * 1e-3)
             roofline = {"bound": "sfu", "kernel": "k_first_order", "achieved": achieved / 1e9, "peak": mufu_peak / 1e9,
-                        "unit": "Gop/s (MUFU.EX2)", "frac": achieved / mufu_peak, "traffic": traffic,
-                        "traffic_note": "dram read+write bytes of one launch, profiles/r1_final_ncu_summary.txt",
+                        "unit": "G exp/s (MUFU.EX2 peak)", "frac": achieved / mufu_peak, "traffic": traffic,
+                        "traffic_source": traffic_source,
                         "hbm": {"algorithmic_bytes": 2 * n4 // world * 16,
                                 "achieved_GBs": 2 * n4 / world * 16 / (first_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
                                 "note": "two float4 output tables per launch; the kernel is SFU-bound, not HBM-bound"},
                         "peak_source": "measured on this pool's B200 by tools/pipe_peaks.cu (profiles/pipe_peaks_b200.json)",
-                        "algorithmic_units": "2 MUFU.EX2 per overall-extinction sample; samples counted on the device",
+                        "algorithmic_units": "2 exponentials per overall-extinction sample (one per scatter component); "
+                                             "samples counted on the device.  One exponential in four is evaluated on "
+                                             "the FMA pipe (ex2_poly2), so the fraction can exceed what the MUFU pipe "
+                                             "alone would allow",
                         "esamples_per_launch": work["esamples_first_order"], "launch_ms": first_ms}
+        # ray-scatter from the dJ table: bound by shared-memory wavefronts.  Floor per 4-D lookup of one warp:
+        # 4 x LDS.128 (16 wavefronts) for the bilinear corners + 1 x STS.128 (4) for its share of the blended tile.
+        roofline_k6 = None
+        if ray_ms and cfg.iterations:
+            lookups = (n4 / world) * 100.0 * cfg.iterations
+            per_s = lookups / (ray_ms * 1e-3)
+            peak = sm_count * clock_hz * 32.0 / 20.0
+            roofline_k6 = {"bound": "shared-memory wavefronts", "kernel": "k_ray_scatter", "achieved": per_s / 1e9,
+                           "peak": peak / 1e9, "unit": "G lookups/s", "frac": per_s / peak,
+                           "model": "1 wavefront / clk / SM; 20 wavefronts per warp-lookup (4 LDS.128 + 1 STS.128), "
+                                    "%d SMs at the measured %.0f MHz" % (sm_count, clock_hz / 1e6),
+                           "lookups_per_pass": lookups / cfg.iterations, "pass_ms": ray_ms / cfg.iterations,
+                           "measured_counters": "profiles/ (ncu): shared wavefronts and thread-instructions per lookup"}
         line = {"metric": METRIC, "value": texels / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "steps": args.steps, "warmup": max(args.warmup, 3) + 2, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
                 "data": "synthetic", "build_time_s": ms_per_step * 1e-3,
                 "config": {"workload": workload, "l2": "512 MiB flush write between timed steps",
-                           "timing": "CUDA events per step on the library stream, max over ranks",
-                           "parallelism": ("single" if world == 1 else "%s%d" % (builder.mode, world)), "wall_s_timed_region": t_wall},
+                           "timing": "CUDA events per step on the builder's stream, max over ranks; one CUDA graph "
+                                     "launch per build",
+                           "exchange": "none (1 GPU)" if world == 1 else
+                                       ("p2p: peer stores over NVLink + flag barriers, no collective" if args.mode == "p2p"
+                                        else "nccl: one all-gather per table"),
+                           "parallelism": ("single" if world == 1 else "%s%d" % (builder.mode, world)),
+                           "wall_s_timed_region": t_wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "stage_ms": {k: round(v, 4) for k, v in stage_dict.items()},
+                "kernel_launches_per_build": launches_per_step,
+                "ray_scatter_pass_texels_per_s": (n4 * cfg.iterations / (ray_ms * 1e-3)) if ray_ms else None,
+                "first_order_texels_per_s": (n4 / (first_ms * 1e-3)) if first_ms else None,
+                "point_scatter_pass_texels_per_s": (n4 * cfg.iterations / (point_ms * 1e-3)) if point_ms else None,
+                "stage_ms": {k: round(v, 4) for k, v in my_stages.items()},
                 "stage_ms_max_over_ranks": {k: round(max(r[k] for r in all_stages), 4) for k in my_stages},
                 "stage_ms_min_over_ranks": {k: round(min(r[k] for r in all_stages), 4) for k in my_stages},
-                "work_per_step": work, "roofline": roofline,
-                "lookup_kernels": {
-                    "note": "issue-slot / FP64 bound gather kernels; no single-pipe roofline applies (ncu: profiles/)",
-                    "ray_scatter_lookups_per_s": (n4 / world) * 100 * cfg.iterations / max(stage_dict.get("ray_scatter", 0.0) * 1e-3, 1e-12),
-                    "point_scatter_direction_evals_per_s": (n4 / world) * 71 * cfg.iterations / max(stage_dict.get("point_scatter", 0.0) * 1e-3, 1e-12)}}
+                "stage_note": "stages from a kernel-by-kernel launch of the same build (events between kernels); "
+                              "ms_per_step is the graph launch",
+                "work_per_step": work, "roofline": roofline, "roofline_k6": roofline_k6}
+        if e2e_pageable:
+            line["e2e_pageable"] = e2e_pageable
+        if identical is not None:
+            line["sharded_identical"] = all(identical.values())
+            line["sharded_identical_detail"] = identical
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1 and args.workload == "shipped":
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
         print(json.dumps(line), flush=True)
     builder.close()
+    failed = identical is not None and not all(identical.values())
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit("the sharded build differs from the single-GPU build: %s" % identical)
 
 
 def main():

@@ -54,7 +54,7 @@ typedef struct {
 /* ---- lifetime (jolt_init / jolt_destroy, jolt.cc:137-182) ---- */
 int atmlut_init(int device);                 /* select the CUDA device, create the stream */
 void atmlut_destroy(void);
-void *atmlut_stream(void);                   /* the library's cudaStream_t (for timing / ordering by the host) */
+void *atmlut_stream(void);                   /* the cudaStream_t of the per-table and batch entry points */
 const char *atmlut_last_error(void);
 int atmlut_device_count(void);
 void atmlut_default_config(atmlut_config *cfg); /* shipped constants, atmosphere_lut.clj:47-63 */
@@ -76,8 +76,8 @@ int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_scatter *sca
                           float *mie_strength);
 
 /* ---- device-resident builder: same computation, split so a host can shard it over GPUs ----
- * Rank r of `world` computes a contiguous slab of every 4-D table; after each table the
- * `allgather` callback (if set) must make buf[0 .. world*bytes_per_rank) identical on all ranks,
+ * All-gather mode: rank r of `world` computes a contiguous slab of every 4-D table; after each table the
+ * `allgather` callback must make buf[0 .. world*bytes_per_rank) identical on all ranks,
  * given that this rank filled buf[rank*bytes_per_rank ..+bytes_per_rank).  `stream` is the
  * cudaStream_t the slab was produced on; the callback must order its work after it. */
 typedef int (*atmlut_allgather_fn)(void *user, void *device_buf, size_t bytes_per_rank, void *stream);
@@ -91,18 +91,34 @@ int atmlut_sphere_directions(int steps, int half, double *dirs, double *weights,
  * elevation_size, padded to per_rank pairs per rank (host-only helper, needs no device) */
 int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *count, int *per_rank);
 /* Peer-to-peer mode (alternative to the all-gather callback; one process per GPU, all on one NVSwitch box,
- * at most 8): every rank exports CUDA IPC handles of its sharded tables (8 handles of 64 bytes), the host
- * exchanges them, and every rank imports all of them in rank order (world * 8 * 64 bytes).  The kernels
- * then store each finished texel into every GPU's table over NVLink, pairs are interleaved over ranks, and
- * a flag barrier replaces each all-gather. */
+ * at most 8): every rank exports CUDA IPC handles of its sharded tables (atmlut_builder_ipc_handle_bytes() bytes:
+ * 64 per table), the host exchanges them, and every rank imports all of them in rank order (world times that many
+ * bytes).  The kernels then store each finished texel into every GPU's table over NVLink, whole height rows are
+ * dealt to the ranks in turn (rank r owns rows r, r + world, ...), a flag barrier replaces each all-gather, and the
+ * file-layout tables are assembled on rank 0 (atmlut_builder_download is valid there only). */
+int atmlut_builder_ipc_handle_bytes(void);
 int atmlut_builder_ipc_export(void *builder, unsigned char *handles, int capacity_bytes);
 int atmlut_builder_ipc_import(void *builder, const unsigned char *all_handles, int world);
 int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *user);
-int atmlut_builder_run(void *builder);        /* asynchronous on the library stream */
+/* options.  ATMLUT_OPT_GRAPH (default 1; ignored in all-gather-callback mode): atmlut_builder_run replays the whole
+ * two-stream build as one CUDA graph, captured on the first run.  ATMLUT_OPT_BARRIER_TIMEOUT_MS (default 10000): how
+ * long a peer-to-peer barrier waits for a peer before the build is failed; all ranks must call run within this time
+ * of each other. */
+#define ATMLUT_OPT_GRAPH 1
+#define ATMLUT_OPT_BARRIER_TIMEOUT_MS 2
+int atmlut_builder_set_option(void *builder, int option, int value);
+int atmlut_builder_run(void *builder);        /* asynchronous on the builder's stream */
+int atmlut_builder_run_timed(void *builder);  /* the same build launched kernel by kernel with per-stage events */
+void *atmlut_builder_stream(void *builder);   /* the builder's cudaStream_t (for timing / ordering by the host) */
 int atmlut_builder_sync(void *builder);       /* wait for the stream */
+/* file layout, as atmlut_generate.  Destinations may be pageable (staged through library-owned pinned buffers) or
+ * page-locked (written by the copy engine directly; see atmlut_host_alloc). */
 int atmlut_builder_download(void *builder, float *transmittance, float *surface_radiance, float *ray_scatter,
-                            float *mie_strength); /* file layout, as atmlut_generate */
-/* per-stage device time of the last run in milliseconds; names via atmlut_builder_stage_name */
+                            float *mie_strength);
+/* page-locked host memory for output tables (a JVM host allocates its output segments here: FFM arenas are pageable) */
+void *atmlut_host_alloc(size_t bytes);
+void atmlut_host_free(void *p);
+/* per-stage device time of the last atmlut_builder_run_timed in milliseconds; names via atmlut_builder_stage_name */
 int atmlut_builder_stage_count(void *builder);
 const char *atmlut_builder_stage_name(void *builder, int stage);
 int atmlut_builder_stage_ms(void *builder, int stage, float *ms);

@@ -50,14 +50,18 @@ class Config(C.Structure):
         return (self.surface_height_size, self.surface_sun_elevation_size)
 
 
+OPT_GRAPH, OPT_BARRIER_TIMEOUT_MS = 1, 2
+
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 # every symbol include/sfsim_atmosphere.h declares
 EXPORTS = [
     "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate", "atmlut_generate_multi",
-    "atmlut_builder_create", "atmlut_sphere_directions", "atmlut_slab", "atmlut_builder_ipc_export", "atmlut_builder_ipc_import",
-    "atmlut_builder_set_allgather", "atmlut_builder_run", "atmlut_builder_sync",
+    "atmlut_builder_create", "atmlut_sphere_directions", "atmlut_slab", "atmlut_builder_ipc_handle_bytes",
+    "atmlut_builder_ipc_export", "atmlut_builder_ipc_import",
+    "atmlut_builder_set_allgather", "atmlut_builder_set_option", "atmlut_builder_run", "atmlut_builder_run_timed",
+    "atmlut_builder_stream", "atmlut_builder_sync", "atmlut_host_alloc", "atmlut_host_free",
     "atmlut_builder_download", "atmlut_builder_stage_count", "atmlut_builder_stage_name", "atmlut_builder_stage_ms",
     "atmlut_builder_work", "atmlut_builder_counter", "atmlut_builder_destroy",
     "atmlut_transmittance_table", "atmlut_surface_radiance_base_table", "atmlut_first_order_tables",
@@ -91,9 +95,14 @@ def load():
                                               C.POINTER(C.c_void_p)]
         for name in ("atmlut_builder_set_allgather",):
             getattr(lib, name).argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p]
-        for name in ("atmlut_builder_run", "atmlut_builder_sync", "atmlut_builder_destroy",
-                     "atmlut_builder_stage_count"):
+        for name in ("atmlut_builder_run", "atmlut_builder_run_timed", "atmlut_builder_sync", "atmlut_builder_destroy",
+                     "atmlut_builder_stage_count", "atmlut_builder_stream"):
             getattr(lib, name).argtypes = [C.c_void_p]
+        lib.atmlut_builder_stream.restype = C.c_void_p
+        lib.atmlut_builder_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.atmlut_host_alloc.restype = C.c_void_p
+        lib.atmlut_host_alloc.argtypes = [C.c_size_t]
+        lib.atmlut_host_free.argtypes = [C.c_void_p]
         lib.atmlut_builder_download.argtypes = [C.c_void_p] * 5
         lib.atmlut_builder_ipc_export.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         lib.atmlut_builder_ipc_import.argtypes = [C.c_void_p, C.c_char_p, C.c_int]

@@ -104,7 +104,7 @@ class AtmosphereLutBuilder:
 
     def _exchange_ipc_handles(self, process_group):
         import torch.distributed as dist
-        mine = C.create_string_buffer(8 * 64)
+        mine = C.create_string_buffer(self.lib.atmlut_builder_ipc_handle_bytes())
         check(self.lib.atmlut_builder_ipc_export(self.handle, mine, len(mine)))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, bytes(mine.raw), group=process_group)
@@ -141,8 +141,20 @@ class AtmosphereLutBuilder:
         check(self.lib.atmlut_builder_set_allgather(self.handle, self._callback, None))
 
     def run(self):
-        """Enqueue one full build on the library stream (asynchronous)."""
+        """Enqueue one full build on the builder's stream (asynchronous; one CUDA graph launch after the first run)."""
         check(self.lib.atmlut_builder_run(self.handle))
+
+    def run_timed(self):
+        """The same build launched kernel by kernel with per-stage events (see stage_times)."""
+        check(self.lib.atmlut_builder_run_timed(self.handle))
+
+    def set_option(self, option, value):
+        check(self.lib.atmlut_builder_set_option(self.handle, int(option), int(value)))
+
+    @property
+    def stream(self):
+        """cudaStream_t of the build (an integer handle)."""
+        return self.lib.atmlut_builder_stream(self.handle)
 
     def sync(self):
         check(self.lib.atmlut_builder_sync(self.handle))
@@ -153,7 +165,7 @@ class AtmosphereLutBuilder:
         return out
 
     def stage_times(self):
-        """[(stage name, device milliseconds)] of the last run."""
+        """[(stage name, device milliseconds)] of the last run_timed()."""
         n = self.lib.atmlut_builder_stage_count(self.handle)
         res = []
         for i in range(n):

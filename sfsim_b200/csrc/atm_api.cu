@@ -35,7 +35,7 @@ int ensure_init() {
 
 cudaStream_t stream() { return g_stream; }
 
-// exp(i/64), i = -256 .. 0, for the kernels' exp_tab (host libm values), one copy per device
+// exp(i/64), i = kExpTabLo .. kExpTabHi, for the kernels' exp_tab (host libm values), one copy per device
 static double *g_exp_table[64] = {};
 
 int exp_table(const double *&table) {
@@ -44,7 +44,7 @@ int exp_table(const double *&table) {
   if (e != cudaSuccess || dev < 0 || dev >= 64) return fail("cannot identify the current device");
   if (!g_exp_table[dev]) {
     std::vector<double> host(kExpTabSize);
-    for (int i = 0; i < kExpTabSize; i++) host[i] = exp((double)(i - (kExpTabSize - 1)) / 64.0);
+    for (int i = 0; i < kExpTabSize; i++) host[i] = exp((double)(i + kExpTabLo) / 64.0);
     e = cudaMalloc((void **)&g_exp_table[dev], kExpTabSize * sizeof(double));
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(exp table)");
     e = cudaMemcpy(g_exp_table[dev], host.data(), kExpTabSize * sizeof(double), cudaMemcpyHostToDevice);
@@ -90,6 +90,17 @@ int make_planet_medium(const atmlut_planet *planet, const atmlut_scatter *scatte
     P.fast.k[c] = (float)(-Rp * log2e / P.medium.scale[c]);
     P.fast.b[c] = (float)(delta * log2e / P.medium.scale[c]);
     for (int i = 0; i < 3; i++) P.fast.ext[c][i] = (float)(P.medium.base[c][i] / P.medium.quotient[c]);
+  }
+  // the hot sampler may take one component's exponentials from the FMA-pipe polynomial (ex2_poly2), which has no
+  // flush to zero: only a component whose exponent stays above -100 over the whole atmosphere qualifies
+  P.fast.poly_exp = -1;
+  for (int c = 1; c >= 0; c--) {
+    if (c >= n) continue;
+    const double min_exponent = -(Rt - Rp) * log2e / P.medium.scale[c];
+    if (P.fast.poly && min_exponent > -100.0) {
+      P.fast.poly_exp = c;
+      break;
+    }
   }
   for (int i = 0; i < 3; i++) P.intensity[i] = 1.0;
   return 0;
@@ -156,11 +167,18 @@ struct Stage {
   cudaEvent_t begin, end;
 };
 
+// number of sharded device tables a rank exposes to its peers (CUDA IPC or peer access), in this order:
+// R1, M1, dJ, dS, dS2, S, S_new (4-D), dE, dE_new (2-D), file_S, file_M (rank 0's are written by everybody), flags
+static const int kPeerTables = 12;
+
 struct Builder {
   Params P;
   int iterations = 0;
   int rank = 0, world = 1;
-  int n_he = 0, he_per_rank = 0, he_begin = 0, he_count = 0;
+  int n_he = 0, he_per_rank = 0;
+  Shard shard = {0, 1, 1};                 // the (height, elevation) pairs this rank integrates
+  int he_count = 0;
+  int h_first = 0, h_stride = 1, h_count = 0;   // height rows whose direction tiles this rank needs
   long long ntex = 0, n4 = 0, n4_pad = 0, nt = 0, ne = 0;
   atmlut_allgather_fn allgather = nullptr;
   void *allgather_user = nullptr;
@@ -168,18 +186,18 @@ struct Builder {
   float4 *T = nullptr, *dE = nullptr, *dE_new = nullptr, *Eacc = nullptr, *Eacc_new = nullptr;
   float4 *R1 = nullptr, *M1 = nullptr, *dS = nullptr, *dS2 = nullptr, *dJ = nullptr, *S = nullptr, *S_new = nullptr;
   int device = 0;                          // CUDA device of this builder
-  cudaStream_t main = nullptr;             // main stream (the library stream, or its own in a multi-GPU group)
-  bool own_main = false;
+  cudaStream_t main = nullptr;             // main stream of the build DAG (owned)
   cudaStream_t side = nullptr;             // second stream of the build DAG
-  // peer-to-peer mode: every sharded table also mapped on the peers (CUDA IPC), flag words for the barrier
+  // peer-to-peer mode: every sharded table also mapped on the peers, flag words for the barrier
   bool p2p = false;
-  int he_stride = 1;
   PeerOut peer_R1 = {}, peer_M1 = {}, peer_dJ = {}, peer_dS = {}, peer_dS2 = {}, peer_S = {}, peer_S_new = {};
-  unsigned epoch_side = 0;
+  PeerOut peer_dE = {}, peer_dE_new = {};
+  float *file_S_root = nullptr, *file_M_root = nullptr;   // rank 0's file-layout tables (every rank fills its pairs)
   unsigned *flags = nullptr;
+  unsigned *epochs = nullptr;              // barrier epochs of the two streams (device memory: graph replay)
   int *error_flag = nullptr;
   unsigned *peer_flags[kMaxPeers] = {};
-  unsigned epoch = 0;
+  int barrier_timeout_ms = 10000;
   std::vector<void *> ipc_opened;
   std::vector<cudaEvent_t> events;         // ordering events between the two streams
   float *file_T = nullptr, *file_E = nullptr, *file_S = nullptr, *file_M = nullptr;
@@ -189,16 +207,26 @@ struct Builder {
   float4 *tiles_a = nullptr, *tiles_b = nullptr;   // blended S tiles per (height, sphere direction)
   HalfDirInfo *half_info = nullptr;
   unsigned long long *counter = nullptr;
+  const double *exp_tab = nullptr;
   std::vector<Stage> stages;
   size_t stage_cursor = 0;
+  bool timed = false;                      // this enqueue records the per-stage events
   bool ran = false;
-  long long launches = 0;   // kernels launched by the last run
+  long long launches = 0;                  // kernels launched by one build
+  // the whole two-stream DAG as one CUDA graph (captured on the first plain run)
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  // pinned staging for downloads into pageable host memory
+  unsigned char *staging[2] = {nullptr, nullptr};
+  cudaEvent_t staging_done[2] = {nullptr, nullptr};
 
   ~Builder() {
     cudaSetDevice(device);
+    if (main) cudaStreamSynchronize(main);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dS2, dJ, S, S_new, file_T, file_E, file_S, file_M,
                     sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
-                    tiles_a, tiles_b};
+                    tiles_a, tiles_b, flags, epochs, error_flag};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     for (auto &s : stages) {
@@ -207,10 +235,12 @@ struct Builder {
     }
     for (auto e : events) cudaEventDestroy(e);
     for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
-    if (flags) cudaFree(flags);
-    if (error_flag) cudaFree(error_flag);
+    for (int i = 0; i < 2; i++) {
+      if (staging[i]) cudaFreeHost(staging[i]);
+      if (staging_done[i]) cudaEventDestroy(staging_done[i]);
+    }
     if (side) cudaStreamDestroy(side);
-    if (own_main && main) cudaStreamDestroy(main);
+    if (main) cudaStreamDestroy(main);
   }
 };
 
@@ -235,15 +265,38 @@ static void slab_of(int n_pairs, int rank, int world, int &begin, int &count, in
   count = std::max(0, std::min(n_pairs, begin + per_rank) - begin);
 }
 
+// NCCL (all-gather) mode and single GPU: a contiguous slab of pairs
+static void use_slab_sharding(Builder &b) {
+  const int E = b.P.shapes.s4[1];
+  int begin = 0;
+  slab_of(b.n_he, b.rank, b.world, begin, b.he_count, b.he_per_rank);
+  b.shard = Shard{begin, 1, 1};
+  b.h_stride = 1;
+  b.h_first = b.he_count > 0 ? begin / E : 0;
+  b.h_count = b.he_count > 0 ? (begin + b.he_count - 1) / E - b.h_first + 1 : 0;
+}
+
+// peer-to-peer mode: whole height rows rank, rank + world, ... (low and high altitudes on every rank; the direction
+// tiles of a row are needed by this rank only)
+static void use_row_sharding(Builder &b) {
+  const int H = b.P.shapes.s4[0], E = b.P.shapes.s4[1];
+  b.h_first = b.rank;
+  b.h_stride = b.world;
+  b.h_count = H > b.rank ? (H - b.rank + b.world - 1) / b.world : 0;
+  b.shard = Shard{b.rank * E, b.world * E, E};
+  b.he_count = b.h_count * E;
+}
+
 static int builder_alloc(Builder &b) {
   const Params &P = b.P;
   b.n_he = P.shapes.s4[0] * P.shapes.s4[1];
   b.ntex = (long long)P.shapes.s4[2] * P.shapes.s4[3];
-  slab_of(b.n_he, b.rank, b.world, b.he_begin, b.he_count, b.he_per_rank);
+  use_slab_sharding(b);
   b.n4 = b.n_he * b.ntex;
   b.n4_pad = (long long)b.he_per_rank * b.world * b.ntex;
   b.nt = (long long)P.shapes.st[0] * P.shapes.st[1];
   b.ne = (long long)P.shapes.se[0] * P.shapes.se[1];
+  CUDA_TRY(cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&b.side, cudaStreamNonBlocking));
   float4 **four[] = {&b.R1, &b.M1, &b.dS, &b.dS2, &b.dJ, &b.S, &b.S_new};
   for (auto p : four) {
@@ -258,9 +311,12 @@ static int builder_alloc(Builder &b) {
   if (dev_alloc(b.file_E, (size_t)b.ne * 3)) return 1;
   if (dev_alloc(b.file_S, (size_t)b.n4 * 3)) return 1;
   if (dev_alloc(b.file_M, (size_t)b.n4 * 3)) return 1;
+  b.file_S_root = b.file_S;
+  b.file_M_root = b.file_M;
   if (dev_alloc(b.counter, 2)) return 1;
-  if (dev_alloc(b.flags, 2 * kMaxPeers) || dev_alloc(b.error_flag, 1)) return 1;
+  if (dev_alloc(b.flags, 2 * kMaxPeers) || dev_alloc(b.epochs, 2) || dev_alloc(b.error_flag, 1)) return 1;
   CUDA_TRY(cudaMemsetAsync(b.flags, 0, 2 * kMaxPeers * sizeof(unsigned), b.main));
+  CUDA_TRY(cudaMemsetAsync(b.epochs, 0, 2 * sizeof(unsigned), b.main));
   CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), b.main));
   b.peer_R1 = local_out(b.R1);
   b.peer_M1 = local_out(b.M1);
@@ -269,6 +325,8 @@ static int builder_alloc(Builder &b) {
   b.peer_dS2 = local_out(b.dS2);
   b.peer_S = local_out(b.S);
   b.peer_S_new = local_out(b.S_new);
+  b.peer_dE = local_out(b.dE);
+  b.peer_dE_new = local_out(b.dE_new);
   std::vector<double> dirs, w;
   sphere_directions(P.shapes.sphere_steps >> 1, P.shapes.sphere_steps, kPi, dirs, w);  // sphere.clj:102-105
   b.n_sphere = (int)w.size();
@@ -282,10 +340,32 @@ static int builder_alloc(Builder &b) {
   if (dev_alloc(b.tiles_a, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
   if (dev_alloc(b.tiles_b, (size_t)P.shapes.s4[0] * b.n_sphere * b.ntex)) return 1;
   if (dev_alloc(b.half_info, (size_t)P.shapes.se[0] * std::max(1, b.n_half))) return 1;
+  if (exp_table(b.exp_tab)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(b.main));
   return 0;
 }
 
+// the peer tables of builder `b` in the order of kPeerTables
+static void peer_table_list(Builder &b, void *ptrs[kPeerTables]) {
+  void *mine[kPeerTables] = {b.R1, b.M1, b.dJ, b.dS, b.dS2, b.S, b.S_new, b.dE, b.dE_new, b.file_S, b.file_M, b.flags};
+  memcpy(ptrs, mine, sizeof mine);
+}
+
+// registers the tables of peer `q` (already mapped into this process / device) with builder `b`
+static void add_peer(Builder &b, int q, void *const ptrs[kPeerTables]) {
+  PeerOut *outs[9] = {&b.peer_R1, &b.peer_M1, &b.peer_dJ, &b.peer_dS, &b.peer_dS2, &b.peer_S, &b.peer_S_new,
+                      &b.peer_dE, &b.peer_dE_new};
+  if (q != b.rank)
+    for (int i = 0; i < 9; i++) outs[i]->p[outs[i]->n++] = (float4 *)ptrs[i];
+  if (q == 0) {
+    b.file_S_root = (float *)ptrs[9];
+    b.file_M_root = (float *)ptrs[10];
+  }
+  b.peer_flags[q] = (unsigned *)ptrs[11];
+}
+
 static int stage_begin(Builder &b, const std::string &name) {
+  if (!b.timed) return 0;
   if (b.stage_cursor == b.stages.size()) {
     Stage s;
     s.name = name;
@@ -298,40 +378,24 @@ static int stage_begin(Builder &b, const std::string &name) {
 }
 
 static int stage_end(Builder &b) {
+  if (!b.timed) return 0;
   CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, b.main));
   b.stage_cursor++;
   return 0;
 }
 
-static int peer_barrier(Builder &b) {
-  b.epoch++;
-  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 0, b.rank, b.world, b.epoch, b.error_flag, b.main));
+static int peer_barrier(Builder &b, int flag_set, cudaStream_t stream) {
+  CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, flag_set, b.rank, b.world, b.epochs, b.error_flag,
+                               b.barrier_timeout_ms, stream));
   b.launches++;
   return 0;
 }
 
-// S += dS (atmosphere_lut.clj:96-97).  Peer-to-peer mode shards it like the integration kernels: every rank
-// re-tabulates its own pairs into all GPUs' copies and a side-stream barrier closes the table.  Otherwise
-// every rank re-tabulates the whole table (cheaper than a collective for this small kernel).
-static int accumulate_s(Builder &b, const float4 *s_cur, const float4 *ds) {
-  const Params &P = b.P;
-  if (b.p2p && b.world > 1) {
-    CUDA_TRY(launch_resample_4d(P, Shard{b.he_begin, b.he_stride}, b.he_count, s_cur, ds, b.peer_S_new, nullptr, b.side));
-    b.epoch_side++;
-    CUDA_TRY(launch_peer_barrier(b.flags, b.peer_flags, 1, b.rank, b.world, b.epoch_side, b.error_flag, b.side));
-    b.launches += 2;
-  } else {
-    CUDA_TRY(launch_resample_4d(P, Shard{0, 1}, b.n_he, s_cur, ds, local_out(b.S_new), nullptr, b.side));
-    b.launches++;
-  }
-  std::swap(b.S, b.S_new);
-  std::swap(b.peer_S, b.peer_S_new);
-  return 0;
-}
-
+// closes a sharded table on the main stream: barrier (the kernels already stored this rank's texels on every GPU)
+// or all-gather callback
 static int gather(Builder &b, float4 *table) {
   if (b.world <= 1) return 0;
-  if (b.p2p) return peer_barrier(b);   // the kernel already stored this rank's texels on every GPU
+  if (b.p2p) return peer_barrier(b, 0, b.main);
   if (!b.allgather) return 0;
   size_t bytes = (size_t)b.he_per_rank * b.ntex * sizeof(float4);
   if (b.allgather(b.allgather_user, table, bytes, (void *)b.main)) return fail("allgather callback failed");
@@ -368,37 +432,41 @@ static int order_after(Builder &b, size_t &cursor, cudaStream_t from, cudaStream
   return 0;
 }
 
-// generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below).
+// generate-atmosphere-luts, atmosphere_lut.clj:43-105 (line numbers in the comments below), enqueued on the
+// builder's two streams.
 //
-// Two streams.  The MAIN stream carries the chain that bounds the build:
+// The MAIN stream carries the chain that bounds the build:
 //     first-order ray scatter -> [ blend tiles -> point scatter (dJ) -> ray scatter (dS) ] x iterations
-// with one all-gather per sharded table.  Everything that merely hangs off that chain runs on the SIDE
-// stream, concurrently with the heavy kernels: the 2-D tables and per-direction constants (needed by the
-// first point-scatter only), surface radiance dE_n = f(dS_{n-1}) (needed by the NEXT point scatter), the
+// with one exchange (flag barrier or all-gather) per sharded table.  Everything that merely hangs off that chain
+// runs on the SIDE stream, concurrently with the heavy kernels: the 2-D tables and per-direction constants (needed
+// by the first point-scatter only), surface radiance dE_n = f(dS_{n-1}) (needed by the NEXT point scatter), the
 // re-tabulated sums E += dE and S += dS (needed only at the very end), and the final file-layout tables.
 // dS and dE are double buffered so the side stream can still read order n-1 while order n is written.
-static int builder_run(Builder &b) {
+//
+// Peer-to-peer mode shards the side stream's kernels as well (surface radiance by texel, the S accumulation and the
+// file-layout tables by pair, the latter stored into rank 0's buffers only) and closes them with ONE side-stream
+// barrier per iteration.
+static int builder_enqueue(Builder &b) {
   const Params &P = b.P;
-  CUDA_TRY(cudaSetDevice(b.device));
   cudaStream_t st = b.main, side = b.side;
   b.stage_cursor = 0;
   b.launches = 0;
   size_t ev = 0;
-  const int E = P.shapes.s4[1];
-  const Shard shard = {b.he_begin, b.he_stride};
-  // heights whose direction tiles this rank needs: its slab's rows, or all of them when pairs are interleaved
-  const int h_first = (b.he_count > 0 && !b.p2p) ? b.he_begin / E : 0;
-  const int h_count = b.he_count <= 0 ? 0 : (b.p2p ? P.shapes.s4[0] : (b.he_begin + b.he_count - 1) / E - h_first + 1);
+  const Shard shard = b.shard;
+  const Shard everything = {0, 1, 1};
+  const bool sharded_side = b.p2p && b.world > 1;
   float4 *dsbuf[2] = {b.dS, b.dS2};
   const PeerOut dsout[2] = {b.peer_dS, b.peer_dS2};
   float4 *debuf[2] = {b.dE, b.dE_new};
+  const PeerOut deout[2] = {b.peer_dE, b.peer_dE_new};
   const int N = b.iterations;
-  const double *etab = nullptr;
-  TRY(exp_table(etab));
+  const double *etab = b.exp_tab;
+  const int e_first = sharded_side ? b.rank : 0, e_stride = sharded_side ? b.world : 1;
 
   CUDA_TRY(cudaMemsetAsync(b.counter, 0, 2 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), st));
   // peer-to-peer mode: nobody may store into a peer's tables before that peer has finished its previous run
-  if (b.p2p && b.world > 1) TRY(peer_barrier(b));
+  if (sharded_side) TRY(peer_barrier(b, 0, st));
   TRY(order_after(b, ev, st, side));   // the side stream starts after whatever the main stream did before
 
   // ---- side: 2-D tables and per-direction constants
@@ -411,23 +479,43 @@ static int builder_run(Builder &b) {
   CUDA_TRY(cudaEventRecord(e_prepared, side));
   LAUNCH(launch_resample_2d(P, 2, b.T, nullptr, nullptr, b.file_T, side));            // :98,102
 
-  // ---- main: first order
+  // ---- main: first order (both tables come out of one kernel: one exchange closes both in peer-to-peer mode)
   TRY(stage_begin(b, "first_order"));
   FirstOrderOut rayleigh = {b.peer_R1, 1, 0};                                         // :68,71,77
   FirstOrderOut mie_strength = {b.peer_M1, 0, 1};                                     // :69,72,78
   LAUNCH(launch_first_order(P, shard, b.he_count, rayleigh, mie_strength, b.counter, st));
   TRY(stage_end(b));
-  TRY(stage_begin(b, "first_order_allgather"));
+  TRY(stage_begin(b, "first_order_exchange"));
   TRY(gather(b, b.R1));
-  TRY(gather(b, b.M1));
+  if (!b.p2p) TRY(gather(b, b.M1));
   TRY(stage_end(b));
 
   SSource ds = {b.R1, b.M1, P.medium.g[0]};                                           // :79-84  dS_0
   const float4 *s_cur = b.R1;                                                         // :85     S_0
   const float4 *e_cur = nullptr;                                                      // :76     E_0 = 0
   std::vector<cudaEvent_t> side_done(N + 1, nullptr);   // side finished reading dS_n
-  std::vector<cudaEvent_t> de_ready(N + 1, nullptr);    // dE_n written
+  std::vector<cudaEvent_t> de_ready(N + 1, nullptr);    // dE_n complete on this GPU
   de_ready[0] = e_prepared;
+
+  // S += dS (atmosphere_lut.clj:96-97): this rank's pairs into every GPU's copy, or the whole table
+  auto accumulate_s = [&](const float4 *ds_tab) -> int {
+    if (sharded_side)
+      LAUNCH(launch_resample_4d(P, shard, b.he_count, s_cur, ds_tab, b.peer_S_new, nullptr, side));
+    else
+      LAUNCH(launch_resample_4d(P, everything, b.n_he, s_cur, ds_tab, local_out(b.S_new), nullptr, side));
+    std::swap(b.S, b.S_new);
+    std::swap(b.peer_S, b.peer_S_new);
+    s_cur = b.S;
+    return 0;
+  };
+  // make-lookup-table of a 4-D table in file layout (:100-101, :104-105): every rank its own pairs, into rank 0
+  auto file_table = [&](const float4 *tab, float *local_file, float *root_file) -> int {
+    if (sharded_side)
+      LAUNCH(launch_resample_4d(P, shard, b.he_count, tab, nullptr, local_out(nullptr), root_file, side));
+    else if (b.rank == 0)
+      LAUNCH(launch_resample_4d(P, everything, b.n_he, tab, nullptr, local_out(nullptr), local_file, side));
+    return 0;
+  };
 
   for (int it = 0; it < N; it++) {                                                    // :86
     char name[64];
@@ -436,38 +524,39 @@ static int builder_run(Builder &b) {
     if (it == 0) CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
     float4 *de_next = debuf[(it + 1) & 1];
     if (b.n_half > 0)
-      LAUNCH(launch_surface_radiance(P, ds, b.half_dirs, b.half_w, b.n_half, b.half_info, de_next, side));  // :89,92
+      LAUNCH(launch_surface_radiance(P, ds, b.half_dirs, b.half_w, b.n_half, b.half_info, e_first, e_stride,
+                                     deout[(it + 1) & 1], side));                     // :89,92
     else
       CUDA_TRY(cudaMemsetAsync(de_next, 0, (size_t)b.ne * sizeof(float4), side));
+    if (it == 0)
+      TRY(file_table(b.M1, b.file_M, b.file_M_root));                                 // :101,105
+    else
+      TRY(accumulate_s(ds.tab_a));                                                    // :96-97
+    if (sharded_side) TRY(peer_barrier(b, 1, side));                                  // dE_{it+1} and S are whole
     TRY(event_at(b, ev++, de_ready[it + 1]));
     CUDA_TRY(cudaEventRecord(de_ready[it + 1], side));
     LAUNCH(launch_resample_2d(P, 1, e_cur, de_next, b.Eacc_new, nullptr, side));      // :94-95
     std::swap(b.Eacc, b.Eacc_new);
     e_cur = b.Eacc;
-    if (it == 0) {
-      LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, b.M1, nullptr, local_out(nullptr), b.file_M, side)); // :101,105
-    } else {
-      TRY(accumulate_s(b, s_cur, ds.tab_a));                                          // :96-97
-      s_cur = b.S;
-    }
     TRY(event_at(b, ev++, side_done[it]));
     CUDA_TRY(cudaEventRecord(side_done[it], side));
 
     // ---- main: dJ_{it+1} = point-scatter(dS_it, dE_it)
     snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
     TRY(stage_begin(b, name));
-    CUDA_TRY(cudaStreamWaitEvent(st, de_ready[it], 0));
-    if (h_count > 0) {
-      LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_a, st));
-      if (ds.tab_b) LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, h_first, h_count, b.tiles_b, st));
+    if (b.h_count > 0) {
+      LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, b.h_first, b.h_stride, b.h_count, b.tiles_a, st));
+      if (ds.tab_b)
+        LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, b.h_first, b.h_stride, b.h_count, b.tiles_b, st));
     }
+    CUDA_TRY(cudaStreamWaitEvent(st, de_ready[it], 0));
     LAUNCH(launch_point_scatter(P, shard, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
                                 debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, etab, b.peer_dJ, st));  // :88,90
     // the next ray-scatter overwrites the buffer of dS_{it-1} (on every GPU in peer-to-peer mode): this
-    // rank's side stream must be done reading it before the barrier / all-gather below lets anyone go on
+    // rank's side stream must be done reading it before the exchange below lets anyone go on
     if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
     TRY(stage_end(b));
-    snprintf(name, sizeof name, "iter%d_point_scatter_allgather", it + 1);
+    snprintf(name, sizeof name, "iter%d_point_scatter_exchange", it + 1);
     TRY(stage_begin(b, name));
     TRY(gather(b, b.dJ));
     TRY(stage_end(b));
@@ -478,7 +567,7 @@ static int builder_run(Builder &b) {
     float4 *ds_next = dsbuf[(it + 1) & 1];
     LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.dJ, etab, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
     TRY(stage_end(b));
-    snprintf(name, sizeof name, "iter%d_ray_scatter_allgather", it + 1);
+    snprintf(name, sizeof name, "iter%d_ray_scatter_exchange", it + 1);
     TRY(stage_begin(b, name));
     TRY(gather(b, ds_next));
     TRY(stage_end(b));
@@ -492,17 +581,67 @@ static int builder_run(Builder &b) {
     CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
     CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), side));       // :76 E = 0
     e_cur = b.Eacc;
-    LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, b.M1, nullptr, local_out(nullptr), b.file_M, side));   // :101,105
+    TRY(file_table(b.M1, b.file_M, b.file_M_root));                                   // :101,105
   } else {
-    TRY(accumulate_s(b, s_cur, ds.tab_a));                                            // :96-97 (last order)
-    s_cur = b.S;
+    TRY(accumulate_s(ds.tab_a));                                                      // :96-97 (last order)
+    if (sharded_side) TRY(peer_barrier(b, 1, side));                                  // S is whole on every GPU
   }
   LAUNCH(launch_resample_2d(P, 1, e_cur, nullptr, nullptr, b.file_E, side));          // :99,103
-  LAUNCH(launch_resample_4d(P, Shard{0, 1}, b.n_he, s_cur, nullptr, local_out(nullptr), b.file_S, side));    // :100,104
+  TRY(file_table(s_cur, b.file_S, b.file_S_root));                                    // :100,104
+  if (sharded_side) TRY(peer_barrier(b, 1, side));                                    // rank 0 holds every pair's texels
   TRY(order_after(b, ev, side, st));
   TRY(stage_end(b));
-  b.ran = true;
   return 0;
+}
+
+// A build leaves b.S / b.S_new (and Eacc / Eacc_new) swapped an odd or even number of times.  Every enqueue must start
+// from the same assignment, or a captured graph would not match a later eager run: remember and restore.
+struct BufferRoles {
+  float4 *S, *S_new, *Eacc, *Eacc_new;
+  PeerOut peer_S, peer_S_new;
+};
+
+static BufferRoles save_roles(const Builder &b) { return BufferRoles{b.S, b.S_new, b.Eacc, b.Eacc_new, b.peer_S, b.peer_S_new}; }
+
+static void restore_roles(Builder &b, const BufferRoles &r) {
+  b.S = r.S;
+  b.S_new = r.S_new;
+  b.Eacc = r.Eacc;
+  b.Eacc_new = r.Eacc_new;
+  b.peer_S = r.peer_S;
+  b.peer_S_new = r.peer_S_new;
+}
+
+// timed = true: eager launches with per-stage events.  Otherwise the DAG is captured once into a CUDA graph and
+// replayed (unless the all-gather callback mode or the option forbids it): one submission instead of ~50 launches
+// and ~25 event edges per build, which matters when a build takes a few milliseconds.
+static int builder_run(Builder &b, bool timed) {
+  CUDA_TRY(cudaSetDevice(b.device));
+  const bool graph = b.use_graph && !timed && !(b.world > 1 && !b.p2p);
+  const BufferRoles roles = save_roles(b);
+  b.timed = timed;
+  int rc = 0;
+  if (!graph) {
+    rc = builder_enqueue(b);
+  } else {
+    if (!b.graph_exec) {
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(b.main, cudaStreamCaptureModeRelaxed));
+      rc = builder_enqueue(b);
+      cudaError_t e = cudaStreamEndCapture(b.main, &g);
+      if (!rc && e != cudaSuccess) rc = fail_cuda(e, "cudaStreamEndCapture");
+      if (!rc) {
+        e = cudaGraphInstantiate(&b.graph_exec, g, 0);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaGraphInstantiate");
+      }
+      if (g) cudaGraphDestroy(g);
+    }
+    if (!rc) CUDA_TRY(cudaGraphLaunch(b.graph_exec, b.main));
+  }
+  restore_roles(b, roles);
+  b.timed = false;
+  if (!rc) b.ran = true;
+  return rc;
 }
 
 }  // namespace atm
@@ -517,6 +656,11 @@ extern "C" int atmlut_device_count(void) {
   return n;
 }
 
+namespace {
+void drop_generate_cache();
+void drop_multi_cache();
+}
+
 extern "C" int atmlut_init(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -524,19 +668,19 @@ extern "C" int atmlut_init(int device) {
     return fail(std::string("no CUDA device available (there is no CPU fallback)") +
                 (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string()));
   if (device < 0 || device >= n) return fail("invalid device index");
-  CUDA_TRY(cudaSetDevice(device));
   if (g_stream && g_device != device) {
+    // the cached one-shot builders live on the old device; builders a host created itself own their streams
+    drop_generate_cache();
+    drop_multi_cache();
+    cudaSetDevice(g_device);
+    cudaStreamSynchronize(g_stream);
     cudaStreamDestroy(g_stream);
     g_stream = nullptr;
   }
+  CUDA_TRY(cudaSetDevice(device));
   if (!g_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   g_device = device;
   return 0;
-}
-
-namespace {
-void drop_generate_cache();
-void drop_multi_cache();
 }
 
 extern "C" void *atmlut_stream(void) { return (void *)g_stream; }
@@ -579,31 +723,38 @@ extern "C" void atmlut_default_config(atmlut_config *cfg) {
 
 // ------------------------------------------------------------------ C ABI: builder
 
+static int new_builder(const atmlut_planet *planet, const atmlut_scatter *scatter, int n, const atmlut_config *cfg,
+                       int rank, int world, int device, Builder **out) {
+  *out = nullptr;
+  if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
+  if (world < 1 || rank < 0 || rank >= world) return fail("invalid rank/world");
+  if (!cfg) return fail("config is NULL");
+  if (cfg->iterations < 0) return fail("iterations must not be negative");
+  CUDA_TRY(cudaSetDevice(device));
+  Builder *b = new Builder();
+  b->device = device;
+  if (make_params(planet, scatter, n, cfg, b->P)) {
+    delete b;
+    return 1;
+  }
+  b->iterations = cfg->iterations;
+  b->rank = rank;
+  b->world = world;
+  if (builder_alloc(*b)) {
+    delete b;
+    return 1;
+  }
+  *out = b;
+  return 0;
+}
+
 extern "C" int atmlut_builder_create(const atmlut_planet *planet, const atmlut_scatter *scatter, int n,
                                      const atmlut_config *cfg, int rank, int world, void **builder) {
   if (!builder) return fail("builder is NULL");
   *builder = nullptr;
   if (ensure_init()) return 1;
-  if (n != 2) return fail("generate-atmosphere-luts needs scatter = [mie rayleigh] (atmosphere_lut.clj:64)");
-  if (world < 1 || rank < 0 || rank >= world) return fail("invalid rank/world");
-  Builder *b = new Builder();
-  if (make_params(planet, scatter, n, cfg, b->P)) {
-    delete b;
-    return 1;
-  }
-  if (cfg->iterations < 0) {
-    delete b;
-    return fail("iterations must not be negative");
-  }
-  b->iterations = cfg->iterations;
-  b->rank = rank;
-  b->world = world;
-  b->device = g_device;
-  b->main = g_stream;
-  if (builder_alloc(*b)) {
-    delete b;
-    return 1;
-  }
+  Builder *b = nullptr;
+  if (new_builder(planet, scatter, n, cfg, rank, world, g_device, &b)) return 1;
   *builder = b;
   return 0;
 }
@@ -634,14 +785,17 @@ extern "C" int atmlut_slab(int n_pairs, int rank, int world, int *begin, int *co
 }
 
 // ---- peer-to-peer mode: CUDA IPC handles of the sharded tables and the barrier flags ----
-static const int kIpcTables = 8;   // R1, M1, dJ, dS, dS2, S, S_new, flags
+
+extern "C" int atmlut_builder_ipc_handle_bytes(void) { return kPeerTables * (int)sizeof(cudaIpcMemHandle_t); }
 
 extern "C" int atmlut_builder_ipc_export(void *builder, unsigned char *handles, int capacity_bytes) {
   Builder *b = (Builder *)builder;
   if (!b || !handles) return fail("invalid argument");
-  if (capacity_bytes < kIpcTables * (int)sizeof(cudaIpcMemHandle_t)) return fail("handle buffer too small");
-  void *ptrs[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->S, b->S_new, b->flags};
-  for (int i = 0; i < kIpcTables; i++) {
+  if (capacity_bytes < atmlut_builder_ipc_handle_bytes()) return fail("handle buffer too small");
+  CUDA_TRY(cudaSetDevice(b->device));
+  void *ptrs[kPeerTables];
+  peer_table_list(*b, ptrs);
+  for (int i = 0; i < kPeerTables; i++) {
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, ptrs[i]));
     memcpy(handles + i * sizeof h, &h, sizeof h);
@@ -656,28 +810,23 @@ extern "C" int atmlut_builder_ipc_import(void *builder, const unsigned char *all
   if (world > kMaxPeers) return fail("peer-to-peer mode supports at most 8 GPUs");
   if (b->p2p) return fail("peer handles were already imported");
   if (b->ran) return fail("import the peer handles before the first run");
-  PeerOut *outs[7] = {&b->peer_R1, &b->peer_M1, &b->peer_dJ, &b->peer_dS, &b->peer_dS2, &b->peer_S, &b->peer_S_new};
+  CUDA_TRY(cudaSetDevice(b->device));
   for (int q = 0; q < world; q++) {
-    void *ptrs[kIpcTables];
+    void *ptrs[kPeerTables];
     if (q == b->rank) {
-      void *mine[kIpcTables] = {b->R1, b->M1, b->dJ, b->dS, b->dS2, b->S, b->S_new, b->flags};
-      memcpy(ptrs, mine, sizeof mine);
+      peer_table_list(*b, ptrs);
     } else {
-      for (int i = 0; i < kIpcTables; i++) {
+      for (int i = 0; i < kPeerTables; i++) {
         cudaIpcMemHandle_t h;
-        memcpy(&h, all_handles + ((size_t)q * kIpcTables + i) * sizeof h, sizeof h);
+        memcpy(&h, all_handles + ((size_t)q * kPeerTables + i) * sizeof h, sizeof h);
         CUDA_TRY(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
         b->ipc_opened.push_back(ptrs[i]);
       }
-      for (int i = 0; i < 7; i++) outs[i]->p[outs[i]->n++] = (float4 *)ptrs[i];
     }
-    b->peer_flags[q] = (unsigned *)ptrs[7];
+    add_peer(*b, q, ptrs);
   }
-  // interleaved pairs: rank r integrates pairs r, r + world, ... (balances cost; no layout constraint here)
   b->p2p = true;
-  b->he_stride = world;
-  b->he_begin = b->rank;
-  b->he_count = b->n_he > b->rank ? (b->n_he - b->rank + world - 1) / world : 0;
+  use_row_sharding(*b);
   return 0;
 }
 
@@ -685,7 +834,9 @@ static int check_peer_error(Builder *b) {
   if (!b->p2p) return 0;
   int err = 0;
   CUDA_TRY(cudaMemcpy(&err, b->error_flag, sizeof err, cudaMemcpyDeviceToHost));
-  if (err) return fail("peer barrier timed out: a peer GPU never arrived");
+  if (err)
+    return fail("peer barrier timed out: a peer GPU never arrived (all ranks must call run within the barrier timeout "
+                "of each other, see ATMLUT_OPT_BARRIER_TIMEOUT_MS)");
   return 0;
 }
 
@@ -697,13 +848,34 @@ extern "C" int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn f
   return 0;
 }
 
-extern "C" int atmlut_builder_run(void *builder) {
+extern "C" int atmlut_builder_set_option(void *builder, int option, int value) {
+  if (!builder) return fail("builder is NULL");
+  Builder *b = (Builder *)builder;
+  if (option == ATMLUT_OPT_GRAPH) {
+    b->use_graph = value != 0;
+  } else if (option == ATMLUT_OPT_BARRIER_TIMEOUT_MS) {
+    if (value < 1) return fail("the barrier timeout must be positive");
+    if (b->graph_exec) return fail("set the barrier timeout before the first run");
+    b->barrier_timeout_ms = value;
+  } else {
+    return fail("unknown option");
+  }
+  return 0;
+}
+
+static int run_checked(void *builder, bool timed) {
   if (!builder) return fail("builder is NULL");
   Builder *b = (Builder *)builder;
   if (b->world > 1 && !b->allgather && !b->p2p)
     return fail("world > 1 needs an allgather callback or imported peer handles");
-  return builder_run(*b);
+  return builder_run(*b, timed);
 }
+
+extern "C" int atmlut_builder_run(void *builder) { return run_checked(builder, false); }
+
+extern "C" int atmlut_builder_run_timed(void *builder) { return run_checked(builder, true); }
+
+extern "C" void *atmlut_builder_stream(void *builder) { return builder ? (void *)((Builder *)builder)->main : nullptr; }
 
 extern "C" int atmlut_builder_sync(void *builder) {
   if (!builder) return fail("builder is NULL");
@@ -713,22 +885,73 @@ extern "C" int atmlut_builder_sync(void *builder) {
   return check_peer_error(b);
 }
 
+// Device -> host copy of one file table.  Pinned or registered destinations (atmlut_host_alloc, cudaHostRegister,
+// torch pinned tensors) are written by the copy engine directly.  Pageable ones -- what a JVM arena or malloc hands
+// out -- would make the driver stage the transfer in small synchronous pieces; instead it is pipelined through two
+// library-owned pinned buffers: the copy engine fills one while the host thread empties the other.
+static const size_t kStagingBytes = 4u << 20;
+
+static int copy_out(Builder *b, void *dst, const void *src, size_t bytes) {
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, dst);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    attr.type = cudaMemoryTypeUnregistered;
+  }
+  if (attr.type != cudaMemoryTypeUnregistered || bytes <= (256u << 10)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->main));
+    return 0;
+  }
+  for (int i = 0; i < 2; i++) {
+    if (!b->staging[i]) CUDA_TRY(cudaMallocHost((void **)&b->staging[i], kStagingBytes));
+    if (!b->staging_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&b->staging_done[i], cudaEventDisableTiming));
+  }
+  const size_t chunks = (bytes + kStagingBytes - 1) / kStagingBytes;
+  auto chunk_bytes = [&](size_t c) { return std::min(kStagingBytes, bytes - c * kStagingBytes); };
+  CUDA_TRY(cudaMemcpyAsync(b->staging[0], src, chunk_bytes(0), cudaMemcpyDeviceToHost, b->main));
+  CUDA_TRY(cudaEventRecord(b->staging_done[0], b->main));
+  for (size_t c = 0; c < chunks; c++) {
+    if (c + 1 < chunks) {
+      CUDA_TRY(cudaMemcpyAsync(b->staging[(c + 1) & 1], (const unsigned char *)src + (c + 1) * kStagingBytes,
+                               chunk_bytes(c + 1), cudaMemcpyDeviceToHost, b->main));
+      CUDA_TRY(cudaEventRecord(b->staging_done[(c + 1) & 1], b->main));
+    }
+    CUDA_TRY(cudaEventSynchronize(b->staging_done[c & 1]));
+    memcpy((unsigned char *)dst + c * kStagingBytes, b->staging[c & 1], chunk_bytes(c));
+  }
+  return 0;
+}
+
 extern "C" int atmlut_builder_download(void *builder, float *transmittance, float *surface_radiance,
                                        float *ray_scatter, float *mie_strength) {
   if (!builder) return fail("builder is NULL");
   Builder *b = (Builder *)builder;
   if (!b->ran) return fail("builder has not run");
+  if (b->world > 1 && b->rank != 0) return fail("the file-layout tables of a sharded build are assembled on rank 0");
   CUDA_TRY(cudaSetDevice(b->device));
-  if (transmittance)
-    CUDA_TRY(cudaMemcpyAsync(transmittance, b->file_T, (size_t)b->nt * 12, cudaMemcpyDeviceToHost, b->main));
-  if (surface_radiance)
-    CUDA_TRY(cudaMemcpyAsync(surface_radiance, b->file_E, (size_t)b->ne * 12, cudaMemcpyDeviceToHost, b->main));
-  if (ray_scatter)
-    CUDA_TRY(cudaMemcpyAsync(ray_scatter, b->file_S, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, b->main));
-  if (mie_strength)
-    CUDA_TRY(cudaMemcpyAsync(mie_strength, b->file_M, (size_t)b->n4 * 12, cudaMemcpyDeviceToHost, b->main));
+  // the large tables first: their staged copies overlap with whatever is still running
+  if (ray_scatter && copy_out(b, ray_scatter, b->file_S, (size_t)b->n4 * 12)) return 1;
+  if (mie_strength && copy_out(b, mie_strength, b->file_M, (size_t)b->n4 * 12)) return 1;
+  if (transmittance && copy_out(b, transmittance, b->file_T, (size_t)b->nt * 12)) return 1;
+  if (surface_radiance && copy_out(b, surface_radiance, b->file_E, (size_t)b->ne * 12)) return 1;
   CUDA_TRY(cudaStreamSynchronize(b->main));
   return check_peer_error(b);
+}
+
+// page-locked host memory for the output tables: the copy engine then writes them directly (a host that cannot
+// pin its own buffers -- the JVM's arenas -- allocates its output segments here)
+extern "C" void *atmlut_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (ensure_init()) return nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail("cudaMallocHost failed");
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void atmlut_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" int atmlut_builder_stage_count(void *builder) {
@@ -744,7 +967,7 @@ extern "C" const char *atmlut_builder_stage_name(void *builder, int stage) {
 
 extern "C" int atmlut_builder_stage_ms(void *builder, int stage, float *ms) {
   Builder *b = (Builder *)builder;
-  if (!b || stage < 0 || stage >= (int)b->stages.size()) return fail("invalid stage");
+  if (!b || stage < 0 || stage >= (int)b->stages.size()) return fail("invalid stage (stages are recorded by run_timed)");
   CUDA_TRY(cudaEventSynchronize(b->stages[stage].end));
   CUDA_TRY(cudaEventElapsedTime(ms, b->stages[stage].begin, b->stages[stage].end));
   return 0;
@@ -753,6 +976,7 @@ extern "C" int atmlut_builder_stage_ms(void *builder, int stage, float *ms) {
 extern "C" int atmlut_builder_work(void *builder, double *esamples, double *lookups4d, double *lookups2d) {
   Builder *b = (Builder *)builder;
   if (!b || !b->ran) return fail("builder has not run");
+  CUDA_TRY(cudaSetDevice(b->device));
   unsigned long long c[2];
   CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, b->main));
   CUDA_TRY(cudaStreamSynchronize(b->main));
@@ -762,7 +986,8 @@ extern "C" int atmlut_builder_work(void *builder, double *esamples, double *look
   const double steps = P.shapes.ray_steps;
   double surf_dirs = 0;  // surface-hitting directions summed over this rank's (height, elevation) pairs
   for (int i = 0; i < b->he_count; i++) {
-    const int he = b->he_begin + i * b->he_stride;
+    const Shard &sh = b->shard;
+    const int he = sh.run <= 1 ? sh.begin + i * sh.stride : sh.begin + (i / sh.run) * sh.stride + i % sh.run;
     for (int d = 0; d < b->n_sphere; d++) surf_dirs += info[(size_t)(he / P.shapes.s4[1]) * b->n_sphere + d].surface;
   }
   double surf_hd = 0;
@@ -785,6 +1010,7 @@ extern "C" int atmlut_builder_counter(void *builder, int which, double *value) {
     return 0;
   }
   if (which < 0 || which > 2) return fail("which must be 0, 1 or 2");
+  CUDA_TRY(cudaSetDevice(b->device));
   unsigned long long c[2];
   CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, b->main));
   CUDA_TRY(cudaStreamSynchronize(b->main));
@@ -795,8 +1021,6 @@ extern "C" int atmlut_builder_counter(void *builder, int which, double *value) {
 extern "C" int atmlut_builder_destroy(void *builder) {
   if (!builder) return 0;
   Builder *b = (Builder *)builder;
-  cudaSetDevice(b->device);
-  cudaStreamSynchronize(b->main);
   delete b;
   if (g_device >= 0) cudaSetDevice(g_device);
   return 0;
@@ -886,27 +1110,22 @@ void drop_multi_cache() {
 
 int create_group(const atmlut_planet *planet, const atmlut_scatter *scatter, const atmlut_config *cfg, int num_gpus,
                  std::vector<Builder *> &group) {
-  for (int d = 0; d < num_gpus; d++) {
-    CUDA_TRY(cudaSetDevice(d));
-    Builder *b = new Builder();
-    group.push_back(b);
-    b->device = d;
-    b->own_main = true;
-    if (make_params(planet, scatter, 2, cfg, b->P)) return 1;
-    CUDA_TRY(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking));
-    b->iterations = cfg->iterations;
-    b->rank = d;
-    b->world = num_gpus;
-    if (builder_alloc(*b)) return 1;
-    CUDA_TRY(cudaStreamSynchronize(b->main));
-  }
-  for (int d = 0; d < num_gpus; d++) {
-    CUDA_TRY(cudaSetDevice(d));
+  for (int d = 0; d < num_gpus; d++)
     for (int q = 0; q < num_gpus; q++) {
       if (q == d) continue;
       int can = 0;
       CUDA_TRY(cudaDeviceCanAccessPeer(&can, d, q));
       if (!can) return fail("GPUs without peer access cannot share one build");
+    }
+  for (int d = 0; d < num_gpus; d++) {
+    Builder *b = nullptr;
+    if (new_builder(planet, scatter, 2, cfg, d, num_gpus, d, &b)) return 1;
+    group.push_back(b);
+  }
+  for (int d = 0; d < num_gpus; d++) {
+    CUDA_TRY(cudaSetDevice(d));
+    for (int q = 0; q < num_gpus; q++) {
+      if (q == d) continue;
       cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
       if (e == cudaErrorPeerAccessAlreadyEnabled)
         cudaGetLastError();
@@ -917,22 +1136,12 @@ int create_group(const atmlut_planet *planet, const atmlut_scatter *scatter, con
   for (int d = 0; d < num_gpus; d++) {
     Builder *b = group[d];
     for (int q = 0; q < num_gpus; q++) {
-      Builder *o = group[q];
-      if (q != d) {
-        b->peer_R1.p[b->peer_R1.n++] = o->R1;
-        b->peer_M1.p[b->peer_M1.n++] = o->M1;
-        b->peer_dJ.p[b->peer_dJ.n++] = o->dJ;
-        b->peer_dS.p[b->peer_dS.n++] = o->dS;
-        b->peer_dS2.p[b->peer_dS2.n++] = o->dS2;
-        b->peer_S.p[b->peer_S.n++] = o->S;
-        b->peer_S_new.p[b->peer_S_new.n++] = o->S_new;
-      }
-      b->peer_flags[q] = o->flags;
+      void *ptrs[kPeerTables];
+      peer_table_list(*group[q], ptrs);
+      add_peer(*b, q, ptrs);
     }
     b->p2p = true;
-    b->he_stride = num_gpus;
-    b->he_begin = d;
-    b->he_count = b->n_he > d ? (b->n_he - d + num_gpus - 1) / num_gpus : 0;
+    use_row_sharding(*b);
   }
   return 0;
 }
@@ -962,9 +1171,10 @@ extern "C" int atmlut_generate_multi(const atmlut_planet *planet, const atmlut_s
     g_multi.scatter[1] = scatter[1];
     g_multi.cfg = *cfg;
   }
+  // every GPU's build is ONE graph launch: the host thread never blocks while a GPU waits for a peer in a barrier
   int rc = 0;
   for (Builder *b : g_multi.group)
-    if (!rc) rc = builder_run(*b);
+    if (!rc) rc = builder_run(*b, false);
   for (Builder *b : g_multi.group)
     if (!rc) rc = atmlut_builder_sync(b);
   if (!rc)
@@ -1057,7 +1267,7 @@ extern "C" int atmlut_first_order_tables(const atmlut_planet *planet, const atml
   if (out_a && d.alloc(ta, (size_t)n4)) return 1;
   if (out_b && d.alloc(tb, (size_t)n4)) return 1;
   FirstOrderOut oa = {local_out(ta), component_a, strength_a}, ob = {local_out(tb), component_b, strength_b};
-  CUDA_TRY(launch_first_order(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
+  CUDA_TRY(launch_first_order(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
   if (out_a && d.download_rgb(ta, n4, out_a)) return 1;
   if (out_b && d.download_rgb(tb, n4, out_b)) return 1;
   CUDA_TRY(cudaStreamSynchronize(g_stream));
@@ -1090,9 +1300,9 @@ extern "C" int atmlut_point_scatter_table(const atmlut_planet *planet, const atm
   float4 *ta = nullptr, *tb = nullptr;
   const size_t tile_count = (size_t)P.shapes.s4[0] * w.size() * P.shapes.s4[2] * P.shapes.s4[3];
   if (d.alloc(ta, tile_count) || (b && d.alloc(tb, tile_count))) return 1;
-  CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), 0, P.shapes.s4[0], ta, g_stream));
-  if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), 0, P.shapes.s4[0], tb, g_stream));
-  CUDA_TRY(launch_point_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
+  CUDA_TRY(launch_blend_dir_tiles(P, a, info, (int)w.size(), 0, 1, P.shapes.s4[0], ta, g_stream));
+  if (b) CUDA_TRY(launch_blend_dir_tiles(P, b, info, (int)w.size(), 0, 1, P.shapes.s4[0], tb, g_stream));
+  CUDA_TRY(launch_point_scatter(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], ta, tb,
                                 ds_b ? P.medium.g[phase_component] : 0.0, e, ddirs, dw, (int)w.size(), info, etab,
                                 local_out(o), g_stream));
   return d.download_rgb(o, n4, out);
@@ -1121,7 +1331,7 @@ extern "C" int atmlut_surface_radiance_table(const atmlut_planet *planet, const 
     return 1;
   CUDA_TRY(launch_surface_radiance_prepare(P, ddirs, (int)w.size(), info, g_stream));
   SSource src = {a, b, ds_b ? P.medium.g[phase_component] : 0.0};
-  CUDA_TRY(launch_surface_radiance(P, src, ddirs, dw, (int)w.size(), info, o, g_stream));
+  CUDA_TRY(launch_surface_radiance(P, src, ddirs, dw, (int)w.size(), info, 0, 1, local_out(o), g_stream));
   return d.download_rgb(o, ne, out);
 }
 
@@ -1136,7 +1346,7 @@ extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlu
   if (d.upload_rgb(dj, n4, j) || d.alloc(o, (size_t)n4)) return 1;
   const double *etab = nullptr;
   if (exp_table(etab)) return 1;
-  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, etab, local_out(o), nullptr, g_stream));
+  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, etab, local_out(o), nullptr, g_stream));
   return d.download_rgb(o, n4, out);
 }
 
@@ -1153,7 +1363,7 @@ extern "C" int atmlut_resample_table(const atmlut_planet *planet, const atmlut_c
   float4 *da = nullptr, *db = nullptr, *o = nullptr;
   if ((a && d.upload_rgb(a, n, da)) || (b && d.upload_rgb(b, n, db)) || d.alloc(o, (size_t)n)) return 1;
   if (which == 0)
-    CUDA_TRY(launch_resample_4d(P, Shard{0, 1}, P.shapes.s4[0] * P.shapes.s4[1], da, db, local_out(o), nullptr, g_stream));
+    CUDA_TRY(launch_resample_4d(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], da, db, local_out(o), nullptr, g_stream));
   else
     CUDA_TRY(launch_resample_2d(P, which, da, db, o, nullptr, g_stream));
   return d.download_rgb(o, n, out);

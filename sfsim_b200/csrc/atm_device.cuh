@@ -9,10 +9,6 @@
 #define ATMLUT_SAMPLER_UNROLL 4
 #endif
 
-#ifndef ATMLUT_SAMPLER_UNROLL
-#define ATMLUT_SAMPLER_UNROLL 4
-#endif
-
 namespace atm {
 
 constexpr int kSamplerUnroll = ATMLUT_SAMPLER_UNROLL;   // 4-sample groups per loop trip of the hot sampler
@@ -36,6 +32,7 @@ struct Fast {
   float k[2];        // -R' * log2(e) / scale_c     (exponent slope in units of h'/R')
   float b[2];        // delta * log2(e) / scale_c   (exponent offset)
   float ext[2][3];   // extinction at h = 0: base_c / quotient_c
+  int poly_exp;      // component whose exp2 the hot sampler may evaluate on the FMA pipe (exponent >= -100), or -1
 };
 
 struct Params {
@@ -128,9 +125,46 @@ __device__ __forceinline__ void densities_from_u2(const Fast &f, float2 u, float
   e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
 }
 
+// 2^a for TWO arguments on the FMA pipe (no MUFU): a = n + f with n = rint(a) taken with the 1.5 * 2^23 magic
+// constant, 2^f by a degree-6 polynomial on [-1/2, 1/2] (max relative error 9.5e-8 in float32, below MUFU.EX2's),
+// and n added to the exponent field with one integer shift-add.  Valid for a > -125 (no flush to zero here).
+// The hot sampler is bound by the MUFU pipe (16 / clk / SM) while the FMA pipe idles half of the time: moving one
+// in four exponentials here balances the two pipes.
+__device__ __forceinline__ float2 ex2_poly2(float2 a) {
+  const float magic = 12582912.0f;   // 1.5 * 2^23
+  const float2 t = __fadd2_rn(a, make_float2(magic, magic));
+  const float2 n = __fadd2_rn(t, make_float2(-magic, -magic));
+  const float2 f = __fadd2_rn(a, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(f, make_float2(0x1.41d332p-13f, 0x1.41d332p-13f), make_float2(0x1.5f456ap-10f, 0x1.5f456ap-10f));
+  p = __ffma2_rn(p, f, make_float2(0x1.3b2dbcp-7f, 0x1.3b2dbcp-7f));
+  p = __ffma2_rn(p, f, make_float2(0x1.c6aed4p-5f, 0x1.c6aed4p-5f));
+  p = __ffma2_rn(p, f, make_float2(0x1.ebfbdap-3f, 0x1.ebfbdap-3f));
+  p = __ffma2_rn(p, f, make_float2(0x1.62e430p-1f, 0x1.62e430p-1f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  // the low mantissa bits of t hold n (two's complement): shifting by 23 drops the magic constant's bits
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
+// densities_from_u2 with the exponential of component `kPolyComp` evaluated by ex2_poly2
+template <int kPolyComp>
+__device__ __forceinline__ void densities_from_u2_poly(const Fast &f, float2 u, float2 &e0, float2 &e1) {
+  float2 q = __ffma2_rn(u, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
+  q = __ffma2_rn(q, u, make_float2(0.0625f, 0.0625f));
+  q = __ffma2_rn(q, u, make_float2(-0.125f, -0.125f));
+  q = __ffma2_rn(q, u, make_float2(0.5f, 0.5f));
+  const float2 hq = __fmul2_rn(u, q);  // h' / R'
+  const float2 a0 = __ffma2_rn(hq, make_float2(f.k[0], f.k[0]), make_float2(f.b[0], f.b[0]));
+  const float2 a1 = __ffma2_rn(hq, make_float2(f.k[1], f.k[1]), make_float2(f.b[1], f.b[1]));
+  e0 = kPolyComp == 0 ? ex2_poly2(a0) : make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+  e1 = kPolyComp == 1 ? ex2_poly2(a1) : make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+}
+
 // Sequential variant (one thread per segment): u(m) advances by forward differences in double, two
 // samples per step (2 DADD per pair); the odd sample's u is the even one's float image plus the float
 // first difference.  Packed accumulators, two independent pairs in flight.
+// kPolyComp >= 0: the second pair of every 4-sample group takes that component's exponentials from ex2_poly2.
+template <int kPolyComp = -1>
 __device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
   if (P.fast.poly) {
     double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // u at m = 1/2
@@ -154,7 +188,10 @@ __device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q,
       step2 += step2_inc;
       d1f += d1f_inc;
       ue = trunc_d2f(u);
-      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
+      if (kPolyComp >= 0)
+        densities_from_u2_poly<kPolyComp>(P.fast, make_float2(ue, ue + d1f), e0, e1);
+      else
+        densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
       acc0b = __fadd2_rn(acc0b, e0);
       acc1b = __fadd2_rn(acc1b, e1);
       u += step2;
@@ -201,22 +238,44 @@ __device__ __forceinline__ void transmittance_rgb(const Fast &f, float c0, float
 
 // ------------------------------------------------------------------ sun-elevation lookup coordinate
 
-// exp(y) for y in [-4, 0] to double accuracy from a table of exp(i/64) (in shared memory, filled with the
-// host's exp) and a degree-4 polynomial on the remainder |y - i/64| <= 1/128 (truncation 2.4e-13 relative).
+// exp(y) for y in [-4, 2.5] to double accuracy from a table of exp(i/64) (in shared memory, filled with the
+// host's exp) and a degree-6 polynomial on the remainder |y - i/64| <= 1/128 (truncation 4e-19 relative, i.e. the
+// result is as good as the table entry: lookups that sit exactly on a table node then carry the same one-ulp
+// weights on the neighbouring rows as the reference's own arithmetic, not 1e-12 ones).
 // The library exp costs ~60 issue slots here (11 polynomial constants reloaded through the uniform datapath);
-// this one costs 12.  Used only for lookup coordinates, which are continuous in it.
-constexpr int kExpTabSize = 4 * 64 + 1;   // i = -256 .. 0
+// this one costs 14.  Used only for lookup coordinates, which are continuous in it.
+constexpr int kExpTabLo = -4 * 64;                     // i = -256 .. 160
+constexpr int kExpTabHi = 160;
+constexpr int kExpTabSize = kExpTabHi - kExpTabLo + 1;
 
 __device__ __forceinline__ double exp_tab(const double *tab, double y) {
   const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of y*64 + magic is rint(y*64)
   const double t = fma(y, 64.0, magic);
-  const int i = __double2loint(t);                    // -256 .. 0
+  const int i = __double2loint(t);                    // -256 .. 160
   const double r = fma(t - magic, -1.0 / 64.0, y);    // y - i/64
-  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return tab[i + (kExpTabSize - 1)] * p;
+  return tab[i - kExpTabLo] * p;
+}
+
+// scale * (1 - exp(y)) from a table that already holds scale * exp(i/64): one fused multiply-add after the
+// polynomial.  y in [-4, 2.5]; the result is <= 0 for y >= 0.
+__device__ __forceinline__ double scaled_one_minus_exp(const double *scaled_tab, double scale, double y) {
+  const double magic = 6755399441055744.0;
+  const double t = fma(y, 64.0, magic);
+  const int i = __double2loint(t);
+  const double r = fma(t - magic, -1.0 / 64.0, y);
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return fma(-scaled_tab[i - kExpTabLo], p, scale);
 }
 
 __device__ __forceinline__ void fill_exp_tab(double *tab, const double *global_tab) {
@@ -274,6 +333,27 @@ __device__ __forceinline__ Axis axis_from_nonneg(double c, int n, double nmax) {
   a.v = min(a.u + 1, n - 1);
   a.s = (float)(i - u);
   return a;
+}
+
+// floor and fraction of a lookup coordinate |c| < 2^31 with the 1.5 * 2^52 rounding constant: three DADD and ONE
+// conversion (of the fraction, which keeps its relative precision) instead of F2I + FRND + F2F, all of which
+// share the 16 / clk / SM conversion pipe.  c < 0 gives u < 0: the caller clamps (interpolate.clj:75-78).
+struct FloorFrac {
+  int u;
+  float s;
+};
+
+__device__ __forceinline__ FloorFrac floor_frac(double c) {
+  const double magic = 6755399441055744.0;
+  const double t = c + magic;
+  const int nearest = __double2loint(t);        // rint(c)
+  const double d = c - (t - magic);             // in [-1/2, 1/2], exact
+  const float df = (float)d;
+  const bool below = __double2hiint(d) < 0;
+  FloorFrac r;
+  r.u = below ? nearest - 1 : nearest;
+  r.s = below ? df + 1.0f : df;
+  return r;
 }
 
 // interpolate.clj:81-84 mix: a (1 - s) + b s

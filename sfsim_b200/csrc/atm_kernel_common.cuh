@@ -1,0 +1,105 @@
+// Device code shared by the table kernels (atm_tables.cu) and the lookup kernels (atm_lookup.cu): the view ray
+// of a (height, elevation) texel pair in shared memory, peer stores, counters.
+#pragma once
+
+#include "atm_device.cuh"
+#include "atm_tables.h"
+
+namespace atm {
+
+// pair index of the i-th CTA of a launch (see Shard)
+__device__ __forceinline__ int shard_pair(const Shard &s, int i) {
+  return s.run <= 1 ? s.begin + i * s.stride : s.begin + (i / s.run) * s.stride + (i % s.run);
+}
+
+// ------------------------------------------------------------------ view ray shared by one CTA
+
+struct ViewRay {
+  double r;        // |x|, x = (r, 0, 0)
+  double vx, vy;   // view direction (atmosphere.clj:256-270)
+  double dx, dy;   // ray end point minus x (atmosphere.clj:196-198)
+  double dlen;     // |d|
+  int above;
+};
+
+struct alignas(16) ViewSmem {
+  ViewRay ray;
+  double pkx[kMaxSteps], pky[kMaxSteps];  // outer sample points p_k
+  double rk2[kMaxSteps];                  // |p_k|^2
+  float cv0[kMaxSteps], cv1[kMaxSteps];   // column densities x -> p_k per component
+  float dens0[kMaxSteps], dens1[kMaxSteps];  // exp(-h(p_k)/scale_c)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Fills ViewSmem for texel pair (h, e) of the 4-D space: the view ray (ray-scatter-backward,
+// atmosphere.clj:401-412; ray end point :196-198), its `steps` outer sample points (ray.clj:19-30)
+// and the transmittance integral x -> p_k for every k (atmosphere.clj:118-125, :199).
+static __device__ void setup_view_ray(const Params &P, int h, int e, ViewSmem &vs, unsigned &esamples) {
+  const int steps = P.shapes.ray_steps;
+  if (threadIdx.x == 0) {
+    V3 x = index_to_height(P.planet, P.shapes.s4[0], (double)h);
+    V3 v;
+    bool above;
+    index_to_elevation(P.planet, P.shapes.s4[1], x.x, (double)e, v, above);
+    V3 end = above ? atmosphere_intersection(P.planet, x, v) : surface_intersection(P.planet, x, v);
+    V3 d = end - x;
+    vs.ray.r = x.x;
+    vs.ray.vx = v.x;
+    vs.ray.vy = v.y;
+    vs.ray.dx = d.x;
+    vs.ray.dy = d.y;
+    vs.ray.dlen = mag(d);
+    vs.ray.above = above ? 1 : 0;
+  }
+  __syncthreads();
+  const ViewRay ray = vs.ray;
+  const double stepsize = 1.0 / (double)steps;
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    double s = (0.5 + (double)k) * stepsize;
+    double px = ray.r + ray.dx * s, py = ray.dy * s;
+    double r2 = px * px + py * py;
+    double hk = sqrt(r2) - P.planet.radius;
+    vs.pkx[k] = px;
+    vs.pky[k] = py;
+    vs.rk2[k] = r2;
+    vs.dens0[k] = (float)exp(-(hk / P.medium.scale[0]));
+    vs.dens1[k] = (float)exp(-(hk / P.medium.scale[1]));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int k = warp; k < steps; k += nwarps) {
+    // segment x -> p_k, direction d_k = p_k - x
+    double dkx = vs.pkx[k] - ray.r, dky = vs.pky[k];
+    double dd = dkx * dkx + dky * dky;
+    Quad q = make_quad(P.fast, ray.r * ray.r, ray.r * dkx, dd, steps);
+    float s0, s1;
+    density_sums_strided(P, q, steps, lane, 32, s0, s1, esamples);
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      double seg = stepsize * sqrt(dd);
+      vs.cv0[k] = (float)((double)s0 * seg);
+      vs.cv1[k] = (float)((double)s1 * seg);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void store_all(const PeerOut &o, size_t idx, float4 v) {
+#pragma unroll 1
+  for (int q = 0; q < o.n; q++) o.p[q][idx] = v;
+}
+
+__device__ __forceinline__ void count_esamples(unsigned long long *counter, unsigned n) {
+  if (!counter) return;
+  n = (unsigned)__reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, (unsigned long long)n);
+}
+
+
+}  // namespace atm

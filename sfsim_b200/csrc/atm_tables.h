@@ -11,11 +11,14 @@ constexpr int kMaxDirs = 1536;  // sphere quadrature directions the point-scatte
 
 constexpr int kMaxPeers = 8;    // GPUs of one NVSwitch box
 
-// Which (height, elevation) pairs a launch integrates: CTA i owns pair begin + i * stride.
-// stride 1 = contiguous slab (NCCL all-gather reassembles the table); stride = world = interleaved pairs
-// (peer-to-peer mode: results are stored straight into every GPU's table, so no layout constraint).
+// Which (height, elevation) pairs a launch integrates: CTA i owns pair begin + (i / run) * stride + i % run.
+//   {0, 1, 1}               every pair (single GPU)
+//   {first, 1, 1}           contiguous slab (NCCL mode: one all-gather reassembles the table)
+//   {r * E, world * E, E}   whole height rows r, r + world, ... (peer-to-peer mode: finished texels are stored into
+//                           every GPU's table, so there is no layout constraint; whole rows keep the pre-blended
+//                           direction tiles of the point-scatter kernel local to the rank that needs them)
 struct Shard {
-  int begin, stride;
+  int begin, stride, run;
 };
 
 // One logical output table: the local copy (p[0]) and the same table on the peer GPUs, mapped through
@@ -73,15 +76,17 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
 // exp_table: device array of kExpTabSize doubles, exp(i/64) for i = -256 .. 0 (see exp_tab)
 cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, const double *exp_table,
                                PeerOut out, unsigned long long *counter, cudaStream_t st);
-// cross-GPU barrier over peer-mapped flag words: signal `epoch` to every peer, wait for every peer's signal
-// flag_set 0 / 1: independent barriers for the main and the side stream (kMaxPeers words each)
+// cross-GPU barrier over peer-mapped flag words: signal the next epoch to every peer, wait for every peer's signal.
+// flag_set 0 / 1: independent barriers for the main and the side stream (kMaxPeers words each).  The epoch lives
+// in device memory (epochs[flag_set], incremented by the kernel), so a captured CUDA graph can be replayed.
+// timeout_ms: a peer that never arrives raises *error_flag instead of hanging the box.
 cudaError_t launch_peer_barrier(unsigned *local_flags, unsigned *const *peer_flags, int flag_set, int rank, int world,
-                                unsigned epoch, int *error_flag, cudaStream_t st);
+                                unsigned *epochs, int *error_flag, int timeout_ms, cudaStream_t st);
 cudaError_t launch_point_scatter_prepare(const Params &P, const double *dirs, int ndirs, DirInfo *info,
                                          cudaStream_t st);
-// blends the tiles of height indices [h_first, h_first + h_count)
+// blends the tiles of height indices h_first, h_first + h_stride, ... (h_count of them)
 cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const DirInfo *info, int ndirs, int h_first,
-                                   int h_count, float4 *tiles, cudaStream_t st);
+                                   int h_stride, int h_count, float4 *tiles, cudaStream_t st);
 // tiles_a / tiles_b: blended [height][direction][light-elevation][heading] tiles of the S source
 cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
                                  const float4 *tiles_b, double phase_g, const float4 *de, const double *dirs,
@@ -90,8 +95,10 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
 size_t ray_scatter_smem(const Params &P);
 cudaError_t launch_surface_radiance_prepare(const Params &P, const double *dirs, int ndirs, HalfDirInfo *info,
                                             cudaStream_t st);
+// texels first, first + stride, ... of the surface-radiance table (every texel for {0, 1})
 cudaError_t launch_surface_radiance(const Params &P, SSource src, const double *dirs, const double *weights,
-                                    int ndirs, const HalfDirInfo *info, float4 *out, cudaStream_t st);
+                                    int ndirs, const HalfDirInfo *info, int first, int stride, PeerOut out,
+                                    cudaStream_t st);
 // re-tabulates the pairs shard.begin + n * shard.stride, n < pair_count
 cudaError_t launch_resample_4d(const Params &P, Shard shard, int pair_count, const float4 *a, const float4 *b,
                                PeerOut out, float *file_out, cudaStream_t st);

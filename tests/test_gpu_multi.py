@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("extra", [["--reduced"], [], ["--reduced", "--mode", "nccl"], ["--mode", "nccl"]])
+@pytest.mark.parametrize("extra", [["--configs", "reduced", "--modes", "p2p"], ["--configs", "shipped", "--modes", "p2p"],
+                                   ["--configs", "reduced", "--modes", "nccl"], ["--configs", "shipped", "--modes", "nccl"]])
 def test_sharded_build_is_identical(extra):
     import torch
     n = torch.cuda.device_count()

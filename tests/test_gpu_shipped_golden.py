@@ -59,10 +59,28 @@ def test_shipped_build_matches_the_oracle_golden(golden, shipped_tables):
     assert float(ls.max()) > 0.1 and float(ls[ls > 0].min()) < 1e-8
 
 
+def rel_err_above_noise(gpu, ref):
+    """Relative error per entry with a floor of 1e-12 x the largest entry of the table.
+
+    An INTERMEDIATE table holds entries that are nothing but rounding noise of the reference's own double arithmetic:
+    a lookup that sits exactly on a table node (e.g. every sample of a vertical view ray has the sun elevation of the
+    texel itself) gives the neighbouring row a weight of one ulp, ~1e-16, and where the node's own row is exactly zero
+    the entry IS that weight times the neighbour -- 7e-26 in the oracle, 2e-25 with a different libm, and whatever
+    the device's ulps make of it.  Such entries (first found at texel 926496 of dS, order 2, by this test) cannot be
+    pinned by any implementation; they are compared absolutely against 1e-16 x max instead.  The FINAL files are sums
+    over all orders in which this noise drowns, and they are held to the strict floor of 1e-20 above."""
+    gpu = np.asarray(gpu, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    assert gpu.shape == ref.shape and np.isfinite(gpu).all()
+    floor = max(FLOOR, 1e-12 * float(np.abs(ref).max()))
+    return float(np.max(np.abs(gpu - ref) / np.maximum(np.abs(ref), floor)))
+
+
 def test_shipped_build_intermediate_orders_match_the_oracle_golden(golden):
     """Order by order: each kernel fed the ORACLE's previous tables is not possible at this size (only sampled texels
     are kept), so the GPU's own chain is compared with the oracle's chain at the sampled texels after every
     iteration -- a deviation shows up at the order it first appears in."""
+    rel_err = rel_err_above_noise
     cfg = _lib.default_config()
     lib = Lib(cfg)
     idx = golden["idx"]
