@@ -286,7 +286,7 @@ def run_b200(args):
     clocks = sampler.stop()
     work = builder.work()
 
-    # ---------------- per-stage times: the same build launched kernel by kernel with events
+    # ---------------- per-stage times: the same build with event records between the stages
     builder.run_timed()
     builder.sync()
     runner.barrier()
@@ -490,8 +490,8 @@ def run_b200(args):
                 "stage_ms": {k: round(v, 4) for k, v in my_stages.items()},
                 "stage_ms_max_over_ranks": {k: round(max(r[k] for r in all_stages), 4) for k in my_stages},
                 "stage_ms_min_over_ranks": {k: round(min(r[k] for r in all_stages), 4) for k in my_stages},
-                "stage_note": "stages from a kernel-by-kernel launch of the same build (events between kernels); "
-                              "ms_per_step is the graph launch",
+                "stage_note": "stages from event-record nodes in a second CUDA graph of the same build, this rank; the "
+                              "exchange stages absorb the waiting for the slowest rank",
                 "work_per_step": work, "roofline": roofline, "roofline_k6": roofline_k6}
         if e2e_pageable:
             line["e2e_pageable"] = e2e_pageable

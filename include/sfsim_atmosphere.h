@@ -108,7 +108,7 @@ int atmlut_builder_set_allgather(void *builder, atmlut_allgather_fn fn, void *us
 #define ATMLUT_OPT_BARRIER_TIMEOUT_MS 2
 int atmlut_builder_set_option(void *builder, int option, int value);
 int atmlut_builder_run(void *builder);        /* asynchronous on the builder's stream */
-int atmlut_builder_run_timed(void *builder);  /* the same build launched kernel by kernel with per-stage events */
+int atmlut_builder_run_timed(void *builder);  /* the same build with per-stage events (see atmlut_builder_stage_ms) */
 void *atmlut_builder_stream(void *builder);   /* the builder's cudaStream_t (for timing / ordering by the host) */
 int atmlut_builder_sync(void *builder);       /* wait for the stream */
 /* file layout, as atmlut_generate.  Destinations may be pageable (staged through library-owned pinned buffers) or

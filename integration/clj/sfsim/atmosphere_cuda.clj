@@ -63,6 +63,11 @@
 
 (defcfn atmlut-device-count "Number of CUDA devices" atmlut_device_count [] ::mem/int)
 
+;; Page-locked host memory for the output tables: FFM arenas hand out pageable memory, which the copy engine cannot
+;; write directly (the library would stage the 25 MB through its own pinned buffers: 14 ms instead of 12 ms per build).
+(defcfn atmlut-host-alloc "Allocate page-locked host memory" atmlut_host_alloc [::mem/long] ::mem/pointer)
+(defcfn atmlut-host-free "Free page-locked host memory" atmlut_host_free [::mem/pointer] ::mem/void)
+
 (defcfn atmlut-generate-
   "generate-atmosphere-luts on the first num-gpus GPUs of the box, driven from this one JVM thread (private)"
   atmlut_generate_multi
@@ -78,28 +83,40 @@
     (throw (RuntimeException. (str "libsfsim_atmosphere: " (atmlut-last-error))))))
 
 
+(defn- generate-on
+  "One call into the library on num-gpus GPUs; outputs are page-locked segments owned by the library"
+  [planet* scatter* n-scatter config* num-gpus sizes]
+  (let [outputs (mapv (fn [n] (mem/reinterpret (atmlut-host-alloc (* 4 n)) (* 4 n))) sizes)]
+    (try
+      (check (apply atmlut-generate- planet* scatter* n-scatter config* num-gpus outputs))
+      (mapv (fn [segment n] (float-array (mem/deserialize-from segment [::mem/array ::mem/float n]))) outputs sizes)
+      (finally
+        (run! atmlut-host-free outputs)))))
+
+
 (defn generate-tables
-  "Compute the four tables on all GPUs of the box (at most 8); returns float arrays in file layout
-   [transmittance surface-radiance ray-scatter mie-strength]"
+  "Compute the four tables on all GPUs of the box (at most 8; one GPU if they cannot access each other's memory);
+   returns float arrays in file layout [transmittance surface-radiance ray-scatter mie-strength]"
   [planet scatter {:keys [height-size elevation-size light-elevation-size heading-size
                           transmittance-height-size transmittance-elevation-size
                           surface-height-size surface-sun-elevation-size
                           ray-steps sphere-steps iterations intensity] :as config}]
   (with-open [arena (mem/confined-arena)]
-    (let [n-t     (* transmittance-height-size transmittance-elevation-size 3)
-          n-e     (* surface-height-size surface-sun-elevation-size 3)
-          n-s     (* height-size elevation-size light-elevation-size heading-size 3)
-          planet* (mem/serialize (planet->c planet) planet-struct arena)
+    (let [n-t      (* transmittance-height-size transmittance-elevation-size 3)
+          n-e      (* surface-height-size surface-sun-elevation-size 3)
+          n-s      (* height-size elevation-size light-elevation-size heading-size 3)
+          planet*  (mem/serialize (planet->c planet) planet-struct arena)
           scatter* (mem/serialize (mapv scatter->c scatter) [::mem/array scatter-struct (count scatter)] arena)
-          config* (mem/serialize (assoc (dissoc config :intensity) :padding 0 :intensity (vec intensity))
-                                 config-struct arena)
-          t*      (mem/alloc (* 4 n-t) arena)
-          e*      (mem/alloc (* 4 n-e) arena)
-          s*      (mem/alloc (* 4 n-s) arena)
-          m*      (mem/alloc (* 4 n-s) arena)]
-      (check (atmlut-generate- planet* scatter* (count scatter) config* (min 8 (atmlut-device-count)) t* e* s* m*))
-      (mapv (fn [segment n] (float-array (mem/deserialize-from segment [::mem/array ::mem/float n])))
-            [t* e* s* m*] [n-t n-e n-s n-s]))))
+          config*  (mem/serialize (assoc (dissoc config :intensity) :padding 0 :intensity (vec intensity))
+                                  config-struct arena)
+          sizes    [n-t n-e n-s n-s]
+          gpus     (min 8 (atmlut-device-count))]
+      (try
+        (generate-on planet* scatter* (count scatter) config* gpus sizes)
+        (catch RuntimeException e
+          (if (and (> gpus 1) (re-find #"peer access" (.getMessage e)))
+            (generate-on planet* scatter* (count scatter) config* 1 sizes)
+            (throw e)))))))
 
 
 (defn generate-atmosphere-luts

@@ -60,6 +60,11 @@ def _pts(a):
     return a
 
 
+def _scatter_key(s):
+    c = _lib.make_scatter(s)
+    return (tuple(c.base), c.scale, c.g, c.quotient)
+
+
 class FirstOrder:
     """First-order point-scatter functions of atmosphere.clj:170-189 bound to their leading arguments, i.e.
     (partial point-scatter-component planet scatter component steps intensity) and friends."""
@@ -171,6 +176,10 @@ def ray_scatter(planet, scatter, steps, point_scatter, x, view_direction, light_
     pl = _lib.make_planet(planet)
     sc = _lib.make_scatter_array(scatter)
     if isinstance(point_scatter, FirstOrder):
+        # component and kind were resolved against the scatter list the FirstOrder source was made with: the same
+        # list must be integrated here, or another component would be picked without a word
+        if [_scatter_key(a) for a in point_scatter.scatter] != [_scatter_key(a) for a in scatter]:
+            raise TypeError("ray_scatter: `scatter` differs from the scatter list of the first-order point-scatter source")
         check(lib.atmlut_ray_scatter_first_order_batch(C.byref(pl), sc, len(scatter), point_scatter.kind,
                                                        point_scatter.component, int(steps),
                                                        _lib.vec3(point_scatter.intensity), len(x), _lib.ptr(x),

@@ -145,7 +145,7 @@ class AtmosphereLutBuilder:
         check(self.lib.atmlut_builder_run(self.handle))
 
     def run_timed(self):
-        """The same build launched kernel by kernel with per-stage events (see stage_times)."""
+        """The same build with per-stage events recorded on the device (see stage_times)."""
         check(self.lib.atmlut_builder_run_timed(self.handle))
 
     def set_option(self, option, value):

@@ -2,6 +2,7 @@
 // buffers, and the host orchestration of generate-atmosphere-luts (atmosphere_lut.clj:43-105).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -206,6 +207,7 @@ struct Builder {
   DirInfo *dir_info = nullptr;
   float4 *tiles_a = nullptr, *tiles_b = nullptr;   // blended S tiles per (height, sphere direction)
   HalfDirInfo *half_info = nullptr;
+  void *ray_samples = nullptr;             // per (pair, outer sample) records of the ray-scatter kernel
   unsigned long long *counter = nullptr;
   const double *exp_tab = nullptr;
   std::vector<Stage> stages;
@@ -215,7 +217,8 @@ struct Builder {
   long long launches = 0;                  // kernels launched by one build
   // the whole two-stream DAG as one CUDA graph (captured on the first plain run)
   bool use_graph = true;
-  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [1]: the same DAG with the per-stage event records
+  bool capturing = false;
   // pinned staging for downloads into pageable host memory
   unsigned char *staging[2] = {nullptr, nullptr};
   cudaEvent_t staging_done[2] = {nullptr, nullptr};
@@ -223,10 +226,11 @@ struct Builder {
   ~Builder() {
     cudaSetDevice(device);
     if (main) cudaStreamSynchronize(main);
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto g : graph_exec)
+      if (g) cudaGraphExecDestroy(g);
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dS2, dJ, S, S_new, file_T, file_E, file_S, file_M,
                     sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
-                    tiles_a, tiles_b, flags, epochs, error_flag};
+                    tiles_a, tiles_b, flags, epochs, error_flag, ray_samples};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     for (auto &s : stages) {
@@ -373,13 +377,20 @@ static int stage_begin(Builder &b, const std::string &name) {
     CUDA_TRY(cudaEventCreate(&s.end));
     b.stages.push_back(s);
   }
-  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].begin, b.main));
+  // inside a capture the record becomes an event-record node of the graph (timing stays valid on replay)
+  if (b.capturing)
+    CUDA_TRY(cudaEventRecordWithFlags(b.stages[b.stage_cursor].begin, b.main, cudaEventRecordExternal));
+  else
+    CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].begin, b.main));
   return 0;
 }
 
 static int stage_end(Builder &b) {
   if (!b.timed) return 0;
-  CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, b.main));
+  if (b.capturing)
+    CUDA_TRY(cudaEventRecordWithFlags(b.stages[b.stage_cursor].end, b.main, cudaEventRecordExternal));
+  else
+    CUDA_TRY(cudaEventRecord(b.stages[b.stage_cursor].end, b.main));
   b.stage_cursor++;
   return 0;
 }
@@ -477,6 +488,14 @@ static int builder_enqueue(Builder &b) {
   cudaEvent_t e_prepared;
   TRY(event_at(b, ev++, e_prepared));
   CUDA_TRY(cudaEventRecord(e_prepared, side));
+  // the view rays of this rank's pairs with everything the ray-scatter passes need per outer sample
+  cudaEvent_t e_rays = nullptr;
+  if (N > 0 && ray_scatter_uses_samples(P)) {
+    if (!b.ray_samples) CUDA_TRY(cudaMalloc(&b.ray_samples, ray_sample_bytes(P, b.he_count)));
+    LAUNCH(launch_ray_prepare(P, shard, b.he_count, b.ray_samples, b.counter + 1, side));
+    TRY(event_at(b, ev++, e_rays));
+    CUDA_TRY(cudaEventRecord(e_rays, side));
+  }
   LAUNCH(launch_resample_2d(P, 2, b.T, nullptr, nullptr, b.file_T, side));            // :98,102
 
   // ---- main: first order (both tables come out of one kernel: one exchange closes both in peer-to-peer mode)
@@ -544,6 +563,7 @@ static int builder_enqueue(Builder &b) {
     // ---- main: dJ_{it+1} = point-scatter(dS_it, dE_it)
     snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
     TRY(stage_begin(b, name));
+    if (it == 0) CUDA_TRY(cudaStreamWaitEvent(st, e_prepared, 0));   // the per-direction constants come from the side stream
     if (b.h_count > 0) {
       LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, b.h_first, b.h_stride, b.h_count, b.tiles_a, st));
       if (ds.tab_b)
@@ -565,7 +585,8 @@ static int builder_enqueue(Builder &b) {
     snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
     TRY(stage_begin(b, name));
     float4 *ds_next = dsbuf[(it + 1) & 1];
-    LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.dJ, etab, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
+    if (it == 0 && e_rays) CUDA_TRY(cudaStreamWaitEvent(st, e_rays, 0));
+    LAUNCH(launch_ray_scatter(P, shard, b.he_count, b.ray_samples, b.dJ, etab, dsout[(it + 1) & 1], b.counter + 1, st));  // :91,93
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_ray_scatter_exchange", it + 1);
     TRY(stage_begin(b, name));
@@ -612,31 +633,35 @@ static void restore_roles(Builder &b, const BufferRoles &r) {
   b.peer_S_new = r.peer_S_new;
 }
 
-// timed = true: eager launches with per-stage events.  Otherwise the DAG is captured once into a CUDA graph and
-// replayed (unless the all-gather callback mode or the option forbids it): one submission instead of ~50 launches
-// and ~25 event edges per build, which matters when a build takes a few milliseconds.
+// The DAG is captured once into a CUDA graph and replayed (unless the all-gather callback mode or the option forbids
+// it): one submission instead of ~50 launches and ~25 event edges per build, which matters when a build takes a few
+// milliseconds.  timed = true: a second graph of the same DAG that also records the per-stage events.
 static int builder_run(Builder &b, bool timed) {
   CUDA_TRY(cudaSetDevice(b.device));
-  const bool graph = b.use_graph && !timed && !(b.world > 1 && !b.p2p);
+  static const bool graph_env = !(getenv("ATMLUT_GRAPH") && atoi(getenv("ATMLUT_GRAPH")) == 0);   // debugging aid
+  const bool graph = b.use_graph && graph_env && !(b.world > 1 && !b.p2p);
   const BufferRoles roles = save_roles(b);
   b.timed = timed;
   int rc = 0;
   if (!graph) {
     rc = builder_enqueue(b);
   } else {
-    if (!b.graph_exec) {
+    cudaGraphExec_t &exec = b.graph_exec[timed ? 1 : 0];
+    if (!exec) {
       cudaGraph_t g = nullptr;
       CUDA_TRY(cudaStreamBeginCapture(b.main, cudaStreamCaptureModeRelaxed));
+      b.capturing = true;
       rc = builder_enqueue(b);
+      b.capturing = false;
       cudaError_t e = cudaStreamEndCapture(b.main, &g);
       if (!rc && e != cudaSuccess) rc = fail_cuda(e, "cudaStreamEndCapture");
       if (!rc) {
-        e = cudaGraphInstantiate(&b.graph_exec, g, 0);
+        e = cudaGraphInstantiate(&exec, g, 0);
         if (e != cudaSuccess) rc = fail_cuda(e, "cudaGraphInstantiate");
       }
       if (g) cudaGraphDestroy(g);
     }
-    if (!rc) CUDA_TRY(cudaGraphLaunch(b.graph_exec, b.main));
+    if (!rc) CUDA_TRY(cudaGraphLaunch(exec, b.main));
   }
   restore_roles(b, roles);
   b.timed = false;
@@ -855,7 +880,7 @@ extern "C" int atmlut_builder_set_option(void *builder, int option, int value) {
     b->use_graph = value != 0;
   } else if (option == ATMLUT_OPT_BARRIER_TIMEOUT_MS) {
     if (value < 1) return fail("the barrier timeout must be positive");
-    if (b->graph_exec) return fail("set the barrier timeout before the first run");
+    if (b->graph_exec[0] || b->graph_exec[1]) return fail("set the barrier timeout before the first run");
     b->barrier_timeout_ms = value;
   } else {
     return fail("unknown option");
@@ -1346,7 +1371,13 @@ extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlu
   if (d.upload_rgb(dj, n4, j) || d.alloc(o, (size_t)n4)) return 1;
   const double *etab = nullptr;
   if (exp_table(etab)) return 1;
-  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], j, etab, local_out(o), nullptr, g_stream));
+  const int n_he = P.shapes.s4[0] * P.shapes.s4[1];
+  unsigned char *samples = nullptr;
+  if (ray_scatter_uses_samples(P)) {
+    if (d.alloc(samples, ray_sample_bytes(P, n_he))) return 1;
+    CUDA_TRY(launch_ray_prepare(P, Shard{0, 1, 1}, n_he, samples, nullptr, g_stream));
+  }
+  CUDA_TRY(launch_ray_scatter(P, Shard{0, 1, 1}, n_he, samples, j, etab, local_out(o), nullptr, g_stream));
   return d.download_rgb(o, n4, out);
 }
 

@@ -335,188 +335,7 @@ __global__ void __launch_bounds__(256, 4) k_point_scatter_v1(Params P, Shard sha
 }
 
 
-// ================================================================== K6, current version
-
-constexpr unsigned kOffMask = (1u << 28) - 1;   // corner-tile offsets (float4 units) fit 28 bits: the table has <= 2^28 texels
-
-// Everything the ray-scatter kernel needs per outer sample p_k that does not depend on the light direction, in one
-// 112-byte record (one base address per sample, fetched with broadcast LDS.128).
-struct alignas(16) RaySample {
-  uint4 rows;       // float4 offsets of the four (height, elevation) corner tiles, in REGISTER-SLOT order;
-                    // bits 28..31 of .x: which slots must be (re)loaded when the loop arrives at this sample
-  float4 w[4];      // T(x -> p_k) rgb * bilinear weight of the corner held in each slot
-  double2 n3;       // -3 p_k / |p_k|: y = n3 . l - 0.6 is the exponent of sun-elevation-to-index
-  double rk;        // |p_k| (exact evaluation next to the lower clamp)
-  double unused;
-};
-
-// dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with point-scatter =
-// the interpolation-table of dJ, interpolate.clj:101-104).  One CTA per (height, elevation) pair, one thread per
-// (light-elevation, heading) texel.
-//
-// Per outer sample k the CTA blends the four (height, elevation) corner tiles of dJ, already multiplied by
-// T(x -> p_k), into one tile in shared memory (double buffered, one barrier per sample); each texel then
-// interpolates the remaining two axes there.  The kernel is bound by L1/shared wavefronts and issue slots, so:
-//  * corner tiles stay in registers while the sample stays inside one (height, elevation) cell, and a step into a
-//    neighbouring cell loads only the two new corners.  Nothing is moved between registers: the two surviving
-//    corners keep their slots and change ROLE, which the set-up accounts for by storing each sample's weights and
-//    offsets in slot order (a height step swaps the roles 00<->10, 01<->11, an elevation step 00<->01, 10<->11;
-//    the swaps commute, so the slot of role r at sample k is r xor the parity of the steps so far);
-//  * the corner weights carry T(x -> p_k), so the lookup accumulates without a further multiply;
-//  * the exponent y and the scaled exponential come from one fused multiply-add each (table pre-multiplied by the
-//    coordinate scale), floor / fraction from the 1.5 * 2^52 rounding constant instead of conversions.
-__global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, const float4 *__restrict__ dj,
-                                                      const double *__restrict__ exp_table, PeerOut out,
-                                                      unsigned long long *counter) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned char s_code[kMaxSteps];
-  const int steps = P.shapes.ray_steps;
-  ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
-  RaySample *sample = reinterpret_cast<RaySample *>(smem_raw + sizeof(ViewSmem));
-  double *s_exp = reinterpret_cast<double *>(sample + steps);                     // exp(i/64) * coordinate scale
-  float4 *tiles = reinterpret_cast<float4 *>(s_exp + ((kExpTabSize + 1) & ~1));
-  const int H = P.shapes.s4[0], E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
-  const int ntex = S * A;
-  const int he = shard_pair(shard, blockIdx.x);
-  const int h = he / E, e = he % E;
-  const int tid = threadIdx.x;
-  unsigned esamples = 0;
-  const double sun_scale = sun_elevation_scale(S);
-  for (int i = tid; i < kExpTabSize; i += blockDim.x) s_exp[i] = exp_table[i] * sun_scale;
-  setup_view_ray(P, h, e, vs, esamples);
-  const ViewRay ray = vs.ray;
-  const V3 v = v3(ray.vx, ray.vy, 0.0);
-  // ---- per outer sample, role order first (blockDim >= 128 and steps <= 256: at most two samples per thread)
-  for (int k = tid; k < steps; k += blockDim.x) {
-    const V3 p = v3(vs.pkx[k], vs.pky[k], 0.0);
-    const Axis ah = axis_from(height_to_index(P.planet, H, p), H);
-    const Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
-    RaySample &r = sample[k];
-    r.rows = make_uint4((unsigned)((ah.u * E + ae.u) * ntex), (unsigned)((ah.u * E + ae.v) * ntex),
-                        (unsigned)((ah.v * E + ae.u) * ntex), (unsigned)((ah.v * E + ae.v) * ntex));
-    float tr[3];
-    transmittance_rgb(P.fast, vs.cv0[k], vs.cv1[k], tr);
-    const float wh1 = ah.s, wh0 = 1.0f - ah.s, we1 = ae.s, we0 = 1.0f - ae.s;
-    const float cw[4] = {wh0 * we0, wh0 * we1, wh1 * we0, wh1 * we1};
-#pragma unroll
-    for (int c = 0; c < 4; c++) r.w[c] = make_float4(tr[0] * cw[c], tr[1] * cw[c], tr[2] * cw[c], 0.0f);
-    const double rk = sqrt(vs.rk2[k]);
-    r.rk = rk;
-    r.n3 = make_double2(-3.0 * (vs.pkx[k] / rk), -3.0 * (vs.pky[k] / rk));
-    r.unused = 0.0;
-  }
-  __syncthreads();
-  // ---- how the corner tiles of sample k follow from those of sample k - 1
-  for (int k = tid; k < steps; k += blockDim.x) {
-    int code = 5;                                           // all four are new
-    if (k > 0) {
-      const uint4 n = sample[k].rows, o = sample[k - 1].rows;
-      if (n.x == o.x && n.y == o.y && n.z == o.z && n.w == o.w) code = 0;       // same cell
-      else if (n.x == o.z && n.y == o.w) code = 1;          // one height row up: roles 10, 11 are new
-      else if (n.z == o.x && n.w == o.y) code = 2;          // one height row down: roles 00, 01 are new
-      else if (n.x == o.y && n.z == o.w) code = 3;          // one elevation column up: roles 01, 11 are new
-      else if (n.y == o.x && n.w == o.z) code = 4;          // one elevation column down: roles 00, 10 are new
-    }
-    s_code[k] = (unsigned char)code;
-  }
-  __syncthreads();
-  // ---- role order -> slot order
-  for (int k = tid; k < steps; k += blockDim.x) {
-    int perm = 0;                                           // slot of role r at sample k = r ^ perm
-    for (int j = 1; j <= k; j++) {
-      const int c = s_code[j];
-      perm ^= (c == 1 || c == 2) ? 2 : ((c == 3 || c == 4) ? 1 : 0);
-    }
-    const int c = s_code[k];
-    const unsigned new_roles = c == 0 ? 0u : c == 1 ? 0xcu : c == 2 ? 0x3u : c == 3 ? 0xau : c == 4 ? 0x5u : 0xfu;
-    RaySample &r = sample[k];
-    const uint4 rows = r.rows;
-    const unsigned ro[4] = {rows.x, rows.y, rows.z, rows.w};
-    const float4 wr[4] = {r.w[0], r.w[1], r.w[2], r.w[3]};
-    unsigned so[4], mask = 0;
-#pragma unroll
-    for (int slot = 0; slot < 4; slot++) {
-      const int role = slot ^ perm;
-      so[slot] = ro[role];
-      r.w[slot] = wr[role];
-      mask |= ((new_roles >> role) & 1u) << slot;
-    }
-    r.rows = make_uint4(so[0] | (mask << 28), so[1], so[2], so[3]);
-  }
-  __syncthreads();
-
-  const bool active = tid < ntex;
-  const int si = active ? tid / A : 0, ai = active ? tid % A : 0;
-  const double ss = index_to_sin_sun_elevation(S, (double)si);
-  const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
-  const Axis aa = axis_from(sun_angle_to_index(A, v, l), A);
-  const float wa1 = aa.s, wa0 = 1.0f - aa.s;
-  const double lx = l.x, ly = l.y;
-  const int s_last = S - 1;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
-  const unsigned utid = (unsigned)tid;   // corner offset + texel stays below 2^29: one 32-bit add, one wide multiply-add
-  if (active) {
-    const uint4 r0 = sample[0].rows;
-    c0 = ldg4(dj + ((r0.x & kOffMask) + utid));
-    c1 = ldg4(dj + (r0.y + utid));
-    c2 = ldg4(dj + (r0.z + utid));
-    c3 = ldg4(dj + (r0.w + utid));
-  }
-#pragma unroll 2
-  for (int k = 0; k < steps; k++) {
-    float4 *tile = tiles + (size_t)(k & 1) * ntex;
-    const RaySample &r = sample[k];
-    if (active) {
-      const float4 w0 = r.w[0], w1 = r.w[1], w2 = r.w[2], w3 = r.w[3];
-      float4 b;
-      b.x = fmaf(w3.x, c3.x, fmaf(w2.x, c2.x, fmaf(w1.x, c1.x, w0.x * c0.x)));
-      b.y = fmaf(w3.y, c3.y, fmaf(w2.y, c2.y, fmaf(w1.y, c1.y, w0.y * c0.y)));
-      b.z = fmaf(w3.z, c3.z, fmaf(w2.z, c2.z, fmaf(w1.z, c1.z, w0.z * c0.z)));
-      b.w = 0.0f;
-      tile[tid] = b;
-    }
-    __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
-    if (active) {
-      if (k + 1 < steps) {
-        // corner tiles of the next sample; the loads fly while this sample's lookup is computed
-        const uint4 rn = sample[k + 1].rows;
-        if (rn.x & (1u << 28)) c0 = ldg4(dj + ((rn.x & kOffMask) + utid));
-        if (rn.x & (2u << 28)) c1 = ldg4(dj + (rn.y + utid));
-        if (rn.x & (4u << 28)) c2 = ldg4(dj + (rn.z + utid));
-        if (rn.x & (8u << 28)) c3 = ldg4(dj + (rn.w + utid));
-      }
-      // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a float32
-      // coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.
-      // y = -3 sin - 0.6 with sin = l . (p_k / |p_k|) (atmosphere.clj:322-326); next to the lower clamp (sin = -0.2,
-      // y = 0, coordinate 0) it is recomputed as the reference writes it, from (dot p l) / (mag p).
-      const double2 n3 = r.n3;
-      double y = fma(lx, n3.x, fma(ly, n3.y, -0.6));
-      if (y > -3e-9) y = (0 - 3 * ((lx * vs.pkx[k] + ly * vs.pky[k]) / r.rk)) - 0.6;
-      // coordinate = scale (1 - exp(y)); <= 0 where the reference's max(0, .) acts
-      FloorFrac fs = floor_frac(scaled_one_minus_exp(s_exp, sun_scale, y));
-      if (fs.u < 0) {
-        fs.u = 0;
-        fs.s = 0.0f;
-      }
-      const int sv = min(fs.u + 1, s_last);
-      const float4 *r0 = tile + fs.u * A, *r1 = tile + sv * A;
-      const float4 v00 = r0[aa.u], v01 = r0[aa.v], v10 = r1[aa.u], v11 = r1[aa.v];
-      const float ws1 = fs.s, ws0 = 1.0f - fs.s;
-      const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
-      acc0 = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, fmaf(w00, v00.x, acc0))));
-      acc1 = fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, fmaf(w00, v00.y, acc1))));
-      acc2 = fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, fmaf(w00, v00.z, acc2))));
-    }
-  }
-  if (active) {
-    const float a = (float)(ray.dlen / (double)steps);
-    store_all(out, (size_t)he * ntex + tid, make_float4(acc0 * a, acc1 * a, acc2 * a, 0.0f));
-  }
-  count_esamples(counter, esamples);
-}
-
-// ================================================================== K4, current version
+// ================================================================== bulk copies (TMA unit) and mbarriers
 
 // ---- bulk copies by the TMA unit, completion on an mbarrier
 
@@ -528,6 +347,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // global -> shared copy of `bytes` (multiple of 16, both addresses 16-byte aligned) issued by ONE thread
@@ -559,8 +382,266 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     if (++spins > (1u << 24)) __trap();
 }
 
-constexpr int kTileStages = 4;           // direction tiles in flight per CTA
-constexpr int kPointScatterThreads = 256;
+
+// coefficients of exp(r) on |r| <= 1/128 (see exp_tab); operands from the constant bank instead of immediates that
+// the compiler rebuilds with uniform moves inside the loops
+__constant__ double kExpPoly[6] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+
+// scale * (1 - exp(y)) from a table that already holds scale * exp(i/64); y in [-4, 2.5]; <= 0 for y >= 0
+__device__ __forceinline__ double coord_from_exponent(const double *scaled_tab, double scale, double y) {
+  const double magic = 6755399441055744.0;            // 1.5 * 2^52: the low word of y*64 + magic is rint(y*64)
+  const double t = fma(y, 64.0, magic);
+  const int i = __double2loint(t);
+  const double r = fma(t - magic, -1.0 / 64.0, y);    // y - i/64
+  double p = fma(r, kExpPoly[0], kExpPoly[1]);
+  p = fma(p, r, kExpPoly[2]);
+  p = fma(p, r, kExpPoly[3]);
+  p = fma(p, r, kExpPoly[4]);
+  p = fma(p, r, kExpPoly[5]);
+  p = fma(p, r, kExpPoly[5]);
+  return fma(-scaled_tab[i - kExpTabLo], p, scale);
+}
+
+// ================================================================== K6, current version
+
+constexpr unsigned kOffMask = (1u << 28) - 1;   // corner-tile offsets (float4 units) fit 28 bits: the table has <= 2^28 texels
+
+// Everything the ray-scatter kernel needs per outer sample p_k that does not depend on the light direction.  The
+// records depend on the (height, elevation) pair only -- not on the scattering order -- so k_ray_prepare writes
+// them once per build and every ray-scatter pass fetches its pair's records with one bulk copy.
+struct alignas(16) RaySample {
+  uint4 rows;       // float4 offsets of the four (height, elevation) corner tiles, in REGISTER-SLOT order
+  float4 cw;        // bilinear weight of the corner held in each slot
+  float4 tr;        // T(x -> p_k) rgb * (ray length / steps); .w: bit mask of the slots the NEXT sample reloads
+  double2 n3;       // -3 p_k / |p_k|: y = n3 . l - 0.6 is the exponent of sun-elevation-to-index
+  double2 pk;       // p_k and ...
+  double rk;        // ... |p_k| for the exact evaluation next to the lower clamp
+  double unused;
+};
+
+// One CTA per (height, elevation) pair: the view ray (setup_view_ray) and, per outer sample, the corner tiles and
+// weights of the dJ lookup's height and elevation axes, T(x -> p_k), and the unit vector of p_k.
+//
+// Corner tiles live in four register slots of the ray-scatter kernel.  While the sample stays inside one
+// (height, elevation) cell nothing is loaded; a step into a neighbouring cell loads the two new corners and the two
+// surviving ones keep their slots and change ROLE (a height step swaps the roles 00<->10, 01<->11, an elevation
+// step 00<->01, 10<->11; the swaps commute, so the slot of role r at sample k is r xor the parity of the steps so
+// far).  Offsets and weights are therefore stored in slot order, with a mask of the slots to load.
+__global__ void __launch_bounds__(256) k_ray_prepare(Params P, Shard shard, RaySample *__restrict__ samples,
+                                                     unsigned long long *counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned char s_code[kMaxSteps];
+  __shared__ unsigned char s_mask[kMaxSteps];
+  ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
+  RaySample *sample = reinterpret_cast<RaySample *>(smem_raw + sizeof(ViewSmem));
+  const int steps = P.shapes.ray_steps;
+  const int H = P.shapes.s4[0], E = P.shapes.s4[1];
+  const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
+  const int he = shard_pair(shard, blockIdx.x);
+  const int h = he / E, e = he % E;
+  const int tid = threadIdx.x;
+  unsigned esamples = 0;
+  setup_view_ray(P, h, e, vs, esamples);
+  const ViewRay ray = vs.ray;
+  const V3 v = v3(ray.vx, ray.vy, 0.0);
+  const float a = (float)(ray.dlen / (double)steps);      // ray.clj:19-30: stepsize * |direction|
+  // ---- role order first
+  for (int k = tid; k < steps; k += blockDim.x) {
+    const V3 p = v3(vs.pkx[k], vs.pky[k], 0.0);
+    const Axis ah = axis_from(height_to_index(P.planet, H, p), H);
+    const Axis ae = axis_from(elevation_to_index(P.planet, E, p, v, ray.above != 0), E);
+    RaySample &r = sample[k];
+    r.rows = make_uint4((unsigned)((ah.u * E + ae.u) * ntex), (unsigned)((ah.u * E + ae.v) * ntex),
+                        (unsigned)((ah.v * E + ae.u) * ntex), (unsigned)((ah.v * E + ae.v) * ntex));
+    const float wh1 = ah.s, wh0 = 1.0f - ah.s, we1 = ae.s, we0 = 1.0f - ae.s;
+    r.cw = make_float4(wh0 * we0, wh0 * we1, wh1 * we0, wh1 * we1);
+    float tr[3];
+    transmittance_rgb(P.fast, vs.cv0[k], vs.cv1[k], tr);
+    r.tr = make_float4(tr[0] * a, tr[1] * a, tr[2] * a, 0.0f);
+    const double rk = sqrt(vs.rk2[k]);
+    r.rk = rk;
+    r.pk = make_double2(vs.pkx[k], vs.pky[k]);
+    r.n3 = make_double2(-3.0 * (vs.pkx[k] / rk), -3.0 * (vs.pky[k] / rk));
+    r.unused = 0.0;
+  }
+  __syncthreads();
+  // ---- how the corner tiles of sample k follow from those of sample k - 1
+  for (int k = tid; k < steps; k += blockDim.x) {
+    int code = 5;                                           // all four are new
+    if (k > 0) {
+      const uint4 n = sample[k].rows, o = sample[k - 1].rows;
+      if (n.x == o.x && n.y == o.y && n.z == o.z && n.w == o.w) code = 0;       // same cell
+      else if (n.x == o.z && n.y == o.w) code = 1;          // one height row up: roles 10, 11 are new
+      else if (n.z == o.x && n.w == o.y) code = 2;          // one height row down: roles 00, 01 are new
+      else if (n.x == o.y && n.z == o.w) code = 3;          // one elevation column up: roles 01, 11 are new
+      else if (n.y == o.x && n.w == o.z) code = 4;          // one elevation column down: roles 00, 10 are new
+    }
+    s_code[k] = (unsigned char)code;
+  }
+  __syncthreads();
+  // ---- role order -> slot order
+  for (int k = tid; k < steps; k += blockDim.x) {
+    int perm = 0;                                           // slot of role r at sample k = r ^ perm
+    for (int j = 1; j <= k; j++) {
+      const int c = s_code[j];
+      perm ^= (c == 1 || c == 2) ? 2 : ((c == 3 || c == 4) ? 1 : 0);
+    }
+    const int c = s_code[k];
+    const unsigned new_roles = c == 0 ? 0u : c == 1 ? 0xcu : c == 2 ? 0x3u : c == 3 ? 0xau : c == 4 ? 0x5u : 0xfu;
+    RaySample &r = sample[k];
+    const uint4 rows = r.rows;
+    const float4 cw = r.cw;
+    const unsigned ro[4] = {rows.x, rows.y, rows.z, rows.w};
+    const float wr[4] = {cw.x, cw.y, cw.z, cw.w};
+    unsigned so[4], mask = 0;
+    float sw[4];
+#pragma unroll
+    for (int slot = 0; slot < 4; slot++) {
+      const int role = slot ^ perm;
+      so[slot] = ro[role];
+      sw[slot] = wr[role];
+      mask |= ((new_roles >> role) & 1u) << slot;
+    }
+    r.rows = make_uint4(so[0], so[1], so[2], so[3]);
+    r.cw = make_float4(sw[0], sw[1], sw[2], sw[3]);
+    s_mask[k] = (unsigned char)mask;
+  }
+  __syncthreads();
+  for (int k = tid; k < steps; k += blockDim.x) {
+    sample[k].tr.w = __uint_as_float(k + 1 < steps ? (unsigned)s_mask[k + 1] : 0u);
+  }
+  __syncthreads();
+  // ---- out: 6 x 16 bytes per sample, coalesced
+  const uint4 *src = reinterpret_cast<const uint4 *>(sample);
+  uint4 *dst = reinterpret_cast<uint4 *>(samples + (size_t)blockIdx.x * steps);
+  const int n16 = steps * (int)(sizeof(RaySample) / 16);
+  for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+  count_esamples(counter, esamples);
+}
+
+// dS[i] = integral-ray over p_k of T(x, p_k) * dJ(p_k, v, l, above)   (atmosphere.clj:192-200 with point-scatter =
+// the interpolation-table of dJ, interpolate.clj:101-104).  One CTA per (height, elevation) pair, one thread per
+// (light-elevation, heading) texel; the pair's RaySample records arrive by one bulk copy.
+//
+// Per outer sample k the CTA blends the four (height, elevation) corner tiles of dJ, times T(x -> p_k), into one
+// tile in shared memory (double buffered, one barrier per sample); each texel then interpolates the remaining two
+// axes there.  The kernel is bound by L1/shared wavefronts and issue slots:
+//  * corner tiles stay in registers across samples (see k_ray_prepare); a cell change loads two new corners;
+//  * per-sample constants are 4 broadcast LDS.128 (a 128-bit broadcast costs two wavefronts), the offsets of the
+//    next sample are only fetched when its reload mask is not empty;
+//  * tile rows are padded by one entry when a row spans a multiple of 32 banks, so that texels of one quarter warp
+//    reading neighbouring rows at the same heading do not collide;
+//  * the exponent y and the scaled exponential come from one fused multiply-add each (table pre-multiplied by the
+//    coordinate scale, polynomial coefficients from the constant bank), floor / fraction from the 1.5 * 2^52
+//    rounding constant instead of conversion instructions.
+__global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, const RaySample *__restrict__ samples,
+                                                      const float4 *__restrict__ dj,
+                                                      const double *__restrict__ exp_table, PeerOut out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int steps = P.shapes.ray_steps;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw);
+  RaySample *sample = reinterpret_cast<RaySample *>(smem_raw + 16);
+  double *s_exp = reinterpret_cast<double *>(sample + steps);                     // exp(i/64) * coordinate scale
+  float4 *tiles = reinterpret_cast<float4 *>(s_exp + ((kExpTabSize + 1) & ~1));
+  const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
+  const int ntex = S * A;
+  const int row_pitch = (A % 8 == 0) ? A + 1 : A;          // float4 entries per tile row
+  const int tile_entries = S * row_pitch;
+  const int he = shard_pair(shard, blockIdx.x);
+  const int h = he / E, e = he % E;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bytes = (unsigned)steps * (unsigned)sizeof(RaySample);
+    mbar_expect_tx(full, bytes);
+    bulk_copy_g2s(sample, samples + (size_t)blockIdx.x * steps, bytes, full);
+  }
+  const double sun_scale = sun_elevation_scale(S);
+  for (int i = tid; i < kExpTabSize; i += blockDim.x) s_exp[i] = exp_table[i] * sun_scale;
+  // this thread's texel: light direction (ray-scatter-backward, atmosphere.clj:401-412) and its heading lookup axis
+  const bool active = tid < ntex;
+  const int si = active ? tid / A : 0, ai = active ? tid % A : 0;
+  V3 x = index_to_height(P.planet, P.shapes.s4[0], (double)h);
+  V3 v;
+  bool above;
+  index_to_elevation(P.planet, E, x.x, (double)e, v, above);
+  const double ss = index_to_sin_sun_elevation(S, (double)si);
+  const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+  const Axis aa = axis_from(sun_angle_to_index(A, v, l), A);
+  const float wa1 = aa.s, wa0 = 1.0f - aa.s;
+  const double lx = l.x, ly = l.y;
+  const int s_last = S - 1;
+  const unsigned utid = (unsigned)tid;   // corner offset + texel stays below 2^29: one 32-bit add, one wide multiply-add
+  const int my_entry = si * row_pitch + ai;
+  __syncthreads();                       // the mbarrier is initialised, the exponential table is filled
+  mbar_wait(full, 0);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+  if (active) {
+    const uint4 r0 = sample[0].rows;
+    c0 = ldg4(dj + (r0.x + utid));
+    c1 = ldg4(dj + (r0.y + utid));
+    c2 = ldg4(dj + (r0.z + utid));
+    c3 = ldg4(dj + (r0.w + utid));
+  }
+#pragma unroll 2
+  for (int k = 0; k < steps; k++) {
+    float4 *tile = tiles + (size_t)(k & 1) * tile_entries;
+    const RaySample &r = sample[k];
+    unsigned next_mask = 0;
+    if (active) {
+      const float4 cw = r.cw, tr = r.tr;
+      next_mask = __float_as_uint(tr.w);
+      float4 b;
+      b.x = tr.x * fmaf(cw.w, c3.x, fmaf(cw.z, c2.x, fmaf(cw.y, c1.x, cw.x * c0.x)));
+      b.y = tr.y * fmaf(cw.w, c3.y, fmaf(cw.z, c2.y, fmaf(cw.y, c1.y, cw.x * c0.y)));
+      b.z = tr.z * fmaf(cw.w, c3.z, fmaf(cw.z, c2.z, fmaf(cw.y, c1.z, cw.x * c0.z)));
+      b.w = 0.0f;
+      tile[my_entry] = b;
+    }
+    __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
+    if (active) {
+      if (next_mask) {
+        // corner tiles of the next sample; the loads fly while this sample's lookup is computed
+        const uint4 rn = sample[k + 1].rows;
+        if (next_mask & 1u) c0 = ldg4(dj + (rn.x + utid));
+        if (next_mask & 2u) c1 = ldg4(dj + (rn.y + utid));
+        if (next_mask & 4u) c2 = ldg4(dj + (rn.z + utid));
+        if (next_mask & 8u) c3 = ldg4(dj + (rn.w + utid));
+      }
+      // The sun-elevation coordinate stays in double: dJ falls by decades across the terminator, so a float32
+      // coordinate (about 1e-5 index units) shows up as 1e-3 relative error in dim texels.
+      // y = -3 sin - 0.6 with sin = l . (p_k / |p_k|) (atmosphere.clj:322-326); where the coordinate is about to be
+      // clamped to 0 (sin = -0.2, y = 0) it is recomputed as the reference writes it, from (dot p l) / (mag p), so
+      // that samples the reference clamps to exactly 0 are clamped here as well.
+      const double2 n3 = r.n3;
+      double y = fma(lx, n3.x, fma(ly, n3.y, -0.6));
+      if (fabs(y) < 3e-9) y = (0 - 3 * ((lx * r.pk.x + ly * r.pk.y) / r.rk)) - 0.6;
+      // coordinate = scale (1 - exp(y)); <= 0 where the reference's max(0, .) acts
+      FloorFrac fs = floor_frac(coord_from_exponent(s_exp, sun_scale, y));
+      if (fs.u < 0) {
+        fs.u = 0;
+        fs.s = 0.0f;
+      }
+      const int sv = min(fs.u + 1, s_last);
+      const float4 *r0 = tile + fs.u * row_pitch, *r1 = tile + sv * row_pitch;
+      const float4 v00 = r0[aa.u], v01 = r0[aa.v], v10 = r1[aa.u], v11 = r1[aa.v];
+      const float ws1 = fs.s, ws0 = 1.0f - fs.s;
+      const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
+      acc0 = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, fmaf(w00, v00.x, acc0))));
+      acc1 = fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, fmaf(w00, v00.y, acc1))));
+      acc2 = fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, fmaf(w00, v00.z, acc2))));
+    }
+  }
+  if (active) store_all(out, (size_t)he * ntex + tid, make_float4(acc0, acc1, acc2, 0.0f));
+}
+
+// ================================================================== K4, current version
+
+constexpr int kTileStages = 6;           // ring of direction tiles per CTA
+constexpr int kPointScatterThreads = 256;                         // consumer threads = texels per CTA
+constexpr int kPointScatterBlock = kPointScatterThreads + 32;     // plus one producer warp
 
 struct alignas(16) PointDir2 {
   double ox, oy;            // omega_d
@@ -586,10 +667,13 @@ __device__ __forceinline__ float4 blend4(float4 v00, float4 v01, float4 v10, flo
 // (atmosphere.clj:203-222).  One CTA per (height, elevation) pair and chunk of 256 texels, one thread per texel,
 // the directions in sequence.  Every thread of the CTA reads the SAME pre-blended [light-elevation][heading] tile
 // for a direction (k_blend_dir_tiles), so the rows of that tile the chunk can touch are streamed into a ring of
-// shared-memory buffers by the TMA unit (cp.async.bulk, one instruction per tile, completion on an mbarrier)
-// while the previous directions are evaluated: a lookup is 4 shared-memory reads with no exposed L2 latency.
+// shared-memory buffers by the TMA unit (cp.async.bulk, one instruction per tile, completion on a "full" mbarrier):
+// a lookup is 4 shared-memory reads with no exposed L2 latency.  A ninth warp is the producer; the eight consumer
+// warps hand buffers back through "empty" mbarriers, so no warp ever waits for another one's arithmetic -- the
+// kernel is latency-bound (double-precision coordinate chains at 24 warps per SM), CTA-wide barriers per direction
+// cost more than anything else.
 template <bool kTwoTables, bool kDeShared>
-__global__ void __launch_bounds__(kPointScatterThreads, 3)
+__global__ void __launch_bounds__(kPointScatterBlock, 3)
     k_point_scatter(Params P, Shard shard, int chunks, int rows_max, const float4 *__restrict__ tiles_a,
                     const float4 *__restrict__ tiles_b, double phase_g, const float4 *__restrict__ de,
                     const double *__restrict__ dirs, const double *__restrict__ weights, int ndirs,
@@ -601,7 +685,8 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
   const int Eh = P.shapes.se[0], Es = P.shapes.se[1];
   const int ntex = S * A;
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw);   // [kTileStages]
-  PointDir2 *pd = reinterpret_cast<PointDir2 *>(smem_raw + 64);
+  unsigned long long *empty = full + kTileStages;                                 // [kTileStages]
+  PointDir2 *pd = reinterpret_cast<PointDir2 *>(smem_raw + 128);
   double *s_exp = reinterpret_cast<double *>(pd + ndirs);
   float4 *s_de = reinterpret_cast<float4 *>(s_exp + ((kExpTabSize + 1) & ~1));
   float4 *stages = s_de + (kDeShared ? Eh * Es : 0);
@@ -610,6 +695,7 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
   const int chunk = blockIdx.x % chunks;
   const int h = he / E, e = he % E;
   const int tid = threadIdx.x;
+  const bool producer = tid >= kPointScatterThreads;
   if (tid == 0) {
     V3 x = index_to_height(P.planet, H, (double)h);
     V3 v;
@@ -620,11 +706,14 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
     s_geom[2] = v.y;
     s_rows[0] = S;
     s_rows[1] = -1;
-    for (int s = 0; s < kTileStages; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < kTileStages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kPointScatterThreads / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const double e_scale = sun_elevation_scale(Es);
-  for (int i = tid; i < kExpTabSize; i += blockDim.x) s_exp[i] = exp_table[i] * e_scale;   // see scaled_one_minus_exp
+  for (int i = tid; i < kExpTabSize; i += blockDim.x) s_exp[i] = exp_table[i] * e_scale;   // see coord_from_exponent
   if (kDeShared)
     for (int i = tid; i < Eh * Es; i += blockDim.x) s_de[i] = ldg4(de + i);
   __syncthreads();
@@ -638,11 +727,13 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
     r.ox = omega.x;
     r.oy = omega.y;
     r.oz = omega.z;
-    // overall-in-scattering (atmosphere.clj:147-151)
+    // overall-in-scattering (atmosphere.clj:147-151); the phase function does not depend on the colour channel
+    double ph[2] = {0.0, 0.0};
+    for (int c = 0; c < P.medium.n; c++) ph[c] = phase(P.medium.g[c], mu);
     for (int ch = 0; ch < 3; ch++) {
       double sum = 0.0;
       for (int c = 0; c < P.medium.n; c++) {
-        double term = scattering(P.medium, c, ch, hx) * phase(P.medium.g[c], mu);
+        double term = scattering(P.medium, c, ch, hx) * ph[c];
         sum = (c == 0) ? term : sum + term;
       }
       r.sc[ch] = (float)(sum * weights[d]);
@@ -667,7 +758,7 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
   }
   // this thread's texel: light direction and the sun-elevation rows of its lookups (the same for every direction)
   const int texel = chunk * kPointScatterThreads + tid;
-  const bool active = texel < ntex;
+  const bool active = !producer && texel < ntex;
   const int si = active ? texel / A : 0, ai = active ? texel % A : 0;
   const double ss = index_to_sin_sun_elevation(S, (double)si);
   const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
@@ -679,17 +770,23 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
   __syncthreads();
   const int row_lo = s_rows[0];
   const int nrows = min(s_rows[1] - row_lo + 1, rows_max);   // rows_max bounds it by construction (see the launcher)
-  const unsigned tile_bytes = (unsigned)(nrows * A) * (unsigned)sizeof(float4);
-  const size_t tile_first = (size_t)h * ndirs * ntex + (size_t)row_lo * A;   // float4 offset of direction 0's rows
-  // producer: thread 0 keeps kTileStages - 1 directions in flight
-  auto issue = [&](int d, int stage) {
-    float4 *dst = stages + (size_t)stage * stage_texels;
-    mbar_expect_tx(&full[stage], kTwoTables ? 2 * tile_bytes : tile_bytes);
-    bulk_copy_g2s(dst, tiles_a + tile_first + (size_t)d * ntex, tile_bytes, &full[stage]);
-    if (kTwoTables) bulk_copy_g2s(dst + nrows * A, tiles_b + tile_first + (size_t)d * ntex, tile_bytes, &full[stage]);
-  };
-  if (tid == 0)
-    for (int d = 0; d < kTileStages - 1 && d < ndirs; d++) issue(d, d);
+
+  if (producer) {
+    // ---- producer warp: one lane streams the tiles, up to kTileStages directions ahead of the slowest consumer warp
+    if (tid == kPointScatterThreads) {
+      const unsigned tile_bytes = (unsigned)(nrows * A) * (unsigned)sizeof(float4);
+      const size_t tile_first = (size_t)h * ndirs * ntex + (size_t)row_lo * A;   // float4 offset of direction 0's rows
+      for (int d = 0; d < ndirs; d++) {
+        const int s = d % kTileStages, use = d / kTileStages;
+        if (use > 0) mbar_wait(&empty[s], (unsigned)(use - 1) & 1u);            // all consumer warps released it
+        float4 *dst = stages + (size_t)s * stage_texels;
+        mbar_expect_tx(&full[s], kTwoTables ? 2 * tile_bytes : tile_bytes);
+        bulk_copy_g2s(dst, tiles_a + tile_first + (size_t)d * ntex, tile_bytes, &full[s]);
+        if (kTwoTables) bulk_copy_g2s(dst + nrows * A, tiles_b + tile_first + (size_t)d * ntex, tile_bytes, &full[s]);
+      }
+    }
+    return;
+  }
 
   const float phase_c0 = (float)((3.0 * (1.0 - phase_g * phase_g)) / (8.0 * kPi * (2.0 + phase_g * phase_g)));
   const double a_half = 0.5 * (double)(A - 1);
@@ -697,6 +794,7 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
   const float ws1 = as.s, ws0 = 1.0f - as.s;
   const int ru = (as.u - row_lo) * A, rv = (as.v - row_lo) * A;
   const double lx = l.x, ly = l.y, lz = l.z;
+  const int lane = tid & 31;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   for (int d0 = 0; d0 < ndirs; d0 += kTileStages) {
     const unsigned parity = (unsigned)(d0 / kTileStages) & 1u;
@@ -704,62 +802,63 @@ __global__ void __launch_bounds__(kPointScatterThreads, 3)
     for (int j = 0; j < kTileStages; j++) {        // the ring position is the unrolled index: static addresses
       const int d = d0 + j;
       if (d >= ndirs) break;
-      __syncthreads();                     // everybody is done with direction d - 1: its buffer may be refilled
-      if (tid == 0 && d + kTileStages - 1 < ndirs) issue(d + kTileStages - 1, (j + kTileStages - 1) % kTileStages);
       mbar_wait(&full[j], parity);
-      if (!active) continue;
-      const float4 *tile = stages + (size_t)j * stage_texels;
-      const PointDir2 &r = pd[d];
-      const double mu = fma(r.oz, lz, fma(r.oy, ly, r.ox * lx));
-      // sun-angle-to-index (atmosphere.clj:368-372); continuous coordinate
-      FloorFrac fa = floor_frac(fma(a_half, mu, a_half));
-      if (fa.u < 0) {
-        fa.u = 0;
-        fa.s = 0.0f;
-      }
-      const int au = min(fa.u, a_last), av = min(fa.u + 1, a_last);
-      const float wa1 = fa.s, wa0 = 1.0f - fa.s;
-      const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
-      float4 sv = blend4(tile[ru + au], tile[ru + av], tile[rv + au], tile[rv + av], w00, w01, w10, w11);
-      if (kTwoTables) {
-        const float4 *tile_b = tile + nrows * A;
-        const float4 m = blend4(tile_b[ru + au], tile_b[ru + av], tile_b[rv + au], tile_b[rv + av], w00, w01, w10, w11);
-        // phase (atmosphere.clj:56-61) with the cancellation-prone base in double and the rest in float
-        const float base = (float)((1.0 + phase_g * phase_g) - 2.0 * phase_g * mu);
-        const float ph = phase_c0 * (float)(1.0 + mu * mu) / (base * sqrtf(base));
-        sv.x = fmaf(m.x, ph, sv.x);
-        sv.y = fmaf(m.y, ph, sv.y);
-        sv.z = fmaf(m.z, ph, sv.z);
-      }
-      if (r.surface) {
-        // surface-radiance (point, l): interpolation-table of dE over surface-radiance-space.  The sine of the sun
-        // elevation at the ground point follows from point = x + t omega: y = -3 sin - 0.6 in two fused
-        // multiply-adds; next to the lower clamp it is recomputed as the reference writes it, from
-        // (dot point l) / (mag point).
-        double y = fma(mu, r.q2, fma(lx, r.q1, -0.6));
-        if (y > -3e-9) y = (0 - 3 * ((r.px * lx + r.py * ly + r.pz * lz) / r.pm)) - 0.6;
-        FloorFrac fe = floor_frac(scaled_one_minus_exp(s_exp, e_scale, y));
-        if (fe.u < 0) {
-          fe.u = 0;
-          fe.s = 0.0f;
+      if (active) {
+        const float4 *tile = stages + (size_t)j * stage_texels;
+        const PointDir2 &r = pd[d];
+        const double mu = fma(r.oz, lz, fma(r.oy, ly, r.ox * lx));
+        // sun-angle-to-index (atmosphere.clj:368-372); continuous coordinate
+        FloorFrac fa = floor_frac(fma(a_half, mu, a_half));
+        if (fa.u < 0) {
+          fa.u = 0;
+          fa.s = 0.0f;
         }
-        const int eu = min(fe.u, es_last), ev = min(fe.u + 1, es_last);
-        const float4 *det = kDeShared ? s_de : de;
-        const float4 *e0 = det + r.ehu * Es, *e1 = det + r.ehv * Es;
-        const float we1 = fe.s, we0 = 1.0f - fe.s, wh1 = r.ehs, wh0 = 1.0f - r.ehs;
-        float4 ev4;
-        if (kDeShared)
-          ev4 = blend4(e0[eu], e0[ev], e1[eu], e1[ev], wh0 * we0, wh0 * we1, wh1 * we0, wh1 * we1);
-        else
-          ev4 = blend4(ldg4(e0 + eu), ldg4(e0 + ev), ldg4(e1 + eu), ldg4(e1 + ev), wh0 * we0, wh0 * we1, wh1 * we0,
-                       wh1 * we1);
-        sv.x = fmaf(r.tb[0], ev4.x, sv.x);
-        sv.y = fmaf(r.tb[1], ev4.y, sv.y);
-        sv.z = fmaf(r.tb[2], ev4.z, sv.z);
+        const int au = min(fa.u, a_last), av = min(fa.u + 1, a_last);
+        const float wa1 = fa.s, wa0 = 1.0f - fa.s;
+        const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
+        float4 sv = blend4(tile[ru + au], tile[ru + av], tile[rv + au], tile[rv + av], w00, w01, w10, w11);
+        if (kTwoTables) {
+          const float4 *tile_b = tile + nrows * A;
+          const float4 m = blend4(tile_b[ru + au], tile_b[ru + av], tile_b[rv + au], tile_b[rv + av], w00, w01, w10, w11);
+          // phase (atmosphere.clj:56-61) with the cancellation-prone base in double and the rest in float
+          const float base = (float)((1.0 + phase_g * phase_g) - 2.0 * phase_g * mu);
+          const float ph = phase_c0 * (float)(1.0 + mu * mu) / (base * sqrtf(base));
+          sv.x = fmaf(m.x, ph, sv.x);
+          sv.y = fmaf(m.y, ph, sv.y);
+          sv.z = fmaf(m.z, ph, sv.z);
+        }
+        if (r.surface) {
+          // surface-radiance (point, l): interpolation-table of dE over surface-radiance-space.  The sine of the sun
+          // elevation at the ground point follows from point = x + t omega: y = -3 sin - 0.6 in two fused
+          // multiply-adds; where the coordinate is about to be clamped to 0 it is recomputed as the reference
+          // writes it, from (dot point l) / (mag point).
+          double y = fma(mu, r.q2, fma(lx, r.q1, -0.6));
+          if (fabs(y) < 3e-9) y = (0 - 3 * ((r.px * lx + r.py * ly + r.pz * lz) / r.pm)) - 0.6;
+          FloorFrac fe = floor_frac(coord_from_exponent(s_exp, e_scale, y));
+          if (fe.u < 0) {
+            fe.u = 0;
+            fe.s = 0.0f;
+          }
+          const int eu = min(fe.u, es_last), ev = min(fe.u + 1, es_last);
+          const float4 *det = kDeShared ? s_de : de;
+          const float4 *e0 = det + r.ehu * Es, *e1 = det + r.ehv * Es;
+          const float we1 = fe.s, we0 = 1.0f - fe.s, wh1 = r.ehs, wh0 = 1.0f - r.ehs;
+          float4 ev4;
+          if (kDeShared)
+            ev4 = blend4(e0[eu], e0[ev], e1[eu], e1[ev], wh0 * we0, wh0 * we1, wh1 * we0, wh1 * we1);
+          else
+            ev4 = blend4(ldg4(e0 + eu), ldg4(e0 + ev), ldg4(e1 + eu), ldg4(e1 + ev), wh0 * we0, wh0 * we1, wh1 * we0,
+                         wh1 * we1);
+          sv.x = fmaf(r.tb[0], ev4.x, sv.x);
+          sv.y = fmaf(r.tb[1], ev4.y, sv.y);
+          sv.z = fmaf(r.tb[2], ev4.z, sv.z);
+        }
+        acc0 = fmaf(r.sc[0], sv.x, acc0);
+        acc1 = fmaf(r.sc[1], sv.y, acc1);
+        acc2 = fmaf(r.sc[2], sv.z, acc2);
       }
-      acc0 = fmaf(r.sc[0], sv.x, acc0);
-      acc1 = fmaf(r.sc[1], sv.y, acc1);
-      acc2 = fmaf(r.sc[2], sv.z, acc2);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[j]);       // this warp is done with the buffer
     }
   }
   if (active) store_all(out, (size_t)he * ntex + texel, make_float4(acc0, acc1, acc2, 0.0f));
@@ -782,27 +881,53 @@ static size_t ray_scatter_smem_v1(const Params &P) {
   return sizeof(ViewSmem) + sizeof(LookupSmem) + 2 * (size_t)P.shapes.s4[2] * P.shapes.s4[3] * sizeof(float4);
 }
 
+static int ray_tile_entries(const Params &P) {
+  const int S = P.shapes.s4[2], A = P.shapes.s4[3];
+  return S * ((A % 8 == 0) ? A + 1 : A);      // must match k_ray_scatter
+}
+
 static size_t ray_scatter_smem_v2(const Params &P) {
-  return sizeof(ViewSmem) + (size_t)P.shapes.ray_steps * sizeof(RaySample) +
-         (size_t)((kExpTabSize + 1) & ~1) * sizeof(double) + 2 * (size_t)P.shapes.s4[2] * P.shapes.s4[3] * sizeof(float4);
+  return 16 + (size_t)P.shapes.ray_steps * sizeof(RaySample) + (size_t)((kExpTabSize + 1) & ~1) * sizeof(double) +
+         2 * (size_t)ray_tile_entries(P) * sizeof(float4);
 }
 
 size_t ray_scatter_smem(const Params &P) { return std::max(ray_scatter_smem_v1(P), ray_scatter_smem_v2(P)); }
 
-cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, const double *exp_table,
-                               PeerOut out, unsigned long long *counter, cudaStream_t st) {
-  if (he_count <= 0) return cudaSuccess;
+static int ray_scatter_variant() {
   static const int variant = env_variant("ATMLUT_K6", 2);
-  const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
-  // more than one texel per thread (tiles above 1024 texels): the generic version walks the tile in chunks
-  const bool v2 = variant >= 2 && ntex <= 1024;
+  return variant;
+}
+
+// the per-sample records live outside the kernel only for tiles of at most 1024 texels (one texel per thread)
+bool ray_scatter_uses_samples(const Params &P) {
+  return ray_scatter_variant() >= 2 && P.shapes.s4[2] * P.shapes.s4[3] <= 1024;
+}
+
+size_t ray_sample_bytes(const Params &P, int he_count) {
+  return (size_t)std::max(he_count, 1) * P.shapes.ray_steps * sizeof(RaySample);
+}
+
+cudaError_t launch_ray_prepare(const Params &P, Shard shard, int he_count, void *samples, unsigned long long *counter,
+                               cudaStream_t st) {
+  if (he_count <= 0 || !ray_scatter_uses_samples(P)) return cudaSuccess;
+  const size_t smem = sizeof(ViewSmem) + (size_t)P.shapes.ray_steps * sizeof(RaySample);
+  cudaError_t e = cudaFuncSetAttribute(k_ray_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_ray_prepare<<<he_count, 256, smem, st>>>(P, shard, (RaySample *)samples, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const void *samples, const float4 *dj,
+                               const double *exp_table, PeerOut out, unsigned long long *counter, cudaStream_t st) {
+  if (he_count <= 0) return cudaSuccess;
+  const bool v2 = ray_scatter_uses_samples(P);
   const size_t smem = v2 ? ray_scatter_smem_v2(P) : ray_scatter_smem_v1(P);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // light-elevation x heading tile too large
   cudaError_t e = v2 ? cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                      : cudaFuncSetAttribute(k_ray_scatter_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (v2)
-    k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, exp_table, out, counter);
+    k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, (const RaySample *)samples, dj, exp_table, out);
   else
     k_ray_scatter_v1<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, exp_table, out, counter);
   return cudaGetLastError();
@@ -830,7 +955,7 @@ static cudaError_t launch_point_scatter_v2(const Params &P, Shard shard, int he_
   cudaError_t e = cudaFuncSetAttribute(k_point_scatter<kTwoTables, kDeShared>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_point_scatter<kTwoTables, kDeShared><<<he_count * chunks, kPointScatterThreads, smem, st>>>(
+  k_point_scatter<kTwoTables, kDeShared><<<he_count * chunks, kPointScatterBlock, smem, st>>>(
       P, shard, chunks, rows_max, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out);
   return cudaGetLastError();
 }
@@ -848,9 +973,9 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
     const int chunks = (ntex + kPointScatterThreads - 1) / kPointScatterThreads;
     const int rows_max = std::min(S, (kPointScatterThreads + A - 1) / A + 3);
     const size_t ne = (size_t)P.shapes.se[0] * P.shapes.se[1];
-    const size_t fixed = 64 + (size_t)ndirs * sizeof(PointDir2) + (size_t)((kExpTabSize + 1) & ~1) * sizeof(double);
+    const size_t fixed = 128 + (size_t)ndirs * sizeof(PointDir2) + (size_t)((kExpTabSize + 1) & ~1) * sizeof(double);
     const size_t stages = (size_t)kTileStages * rows_max * A * sizeof(float4) * (tiles_b ? 2 : 1);
-    const bool de_shared = ne * sizeof(float4) <= 32 * 1024 && fixed + stages + ne * sizeof(float4) <= 72 * 1024;
+    const bool de_shared = ne * sizeof(float4) <= 32 * 1024 && fixed + stages + ne * sizeof(float4) <= 75 * 1024;
     const size_t smem = fixed + stages + (de_shared ? ne * sizeof(float4) : 0);
     if (smem <= 227 * 1024) {
       if (tiles_b)

@@ -486,8 +486,10 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
     }
   }
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
-  // one exponential in four on the FMA pipe (ex2_poly2) when the medium allows it; ATMLUT_K3_POLY=0 switches it off
-  static const int want_poly = env_int("ATMLUT_K3_POLY", 1);
+  // ATMLUT_K3_POLY=1: one exponential in four on the FMA pipe (ex2_poly2).  Measured on B200: 5.00 ms against 4.22 ms
+  // with all exponentials on the MUFU pipe -- packed FFMA2 halves the issue slots, not the FMA-pipe cycles, and
+  // that pipe is already 52 % busy -- so it is off by default and kept only for the comparison.
+  static const int want_poly = env_int("ATMLUT_K3_POLY", 0);
   const int poly = want_poly ? P.fast.poly_exp : -1;
   if (poly == 1)
     k_first_order<1><<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);

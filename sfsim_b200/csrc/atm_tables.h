@@ -73,9 +73,16 @@ cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_
 cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st);
 cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
                                unsigned long long *counter, cudaStream_t st);
-// exp_table: device array of kExpTabSize doubles, exp(i/64) for i = -256 .. 0 (see exp_tab)
-cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const float4 *dj, const double *exp_table,
-                               PeerOut out, unsigned long long *counter, cudaStream_t st);
+// exp_table: device array of kExpTabSize doubles, exp(i/64) for i = kExpTabLo .. kExpTabHi (see exp_tab)
+// The ray-scatter kernel reads per-(pair, outer sample) records that do not depend on the scattering order:
+// launch_ray_prepare writes them once per build (ray_sample_bytes(P, he_count) bytes for the same shard and
+// he_count, slot i = the i-th pair of the shard); counter receives the overall-extinction samples it evaluated.
+bool ray_scatter_uses_samples(const Params &P);
+size_t ray_sample_bytes(const Params &P, int he_count);
+cudaError_t launch_ray_prepare(const Params &P, Shard shard, int he_count, void *samples, unsigned long long *counter,
+                               cudaStream_t st);
+cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const void *samples, const float4 *dj,
+                               const double *exp_table, PeerOut out, unsigned long long *counter, cudaStream_t st);
 // cross-GPU barrier over peer-mapped flag words: signal the next epoch to every peer, wait for every peer's signal.
 // flag_set 0 / 1: independent barriers for the main and the side stream (kMaxPeers words each).  The epoch lives
 // in device memory (epochs[flag_set], incremented by the kernel), so a captured CUDA graph can be replayed.

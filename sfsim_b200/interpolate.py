@@ -161,8 +161,26 @@ def _config_for(shape4=None, shape_t=None, shape_e=None, **kw):
                             surface_radiance_shape=shape_e or cfg.surface_radiance_shape, **kw)
 
 
-def _table_of(src):
-    return _lib.f32(src.table if isinstance(src, InterpolationTable) else src)
+def _table_of(src, shape=None, what="source table"):
+    """float32 host table of an InterpolationTable or a plain array.  The C entry points take no table-shape
+    argument and read prod(shape) * 3 floats from the pointer, so a table of any other shape is refused here."""
+    tab = _lib.f32(src.table if isinstance(src, InterpolationTable) else src)
+    if shape is not None and tuple(tab.shape) != tuple(shape) + (3,):
+        raise TypeError("%s has shape %s, but the space being tabulated needs %s" %
+                        (what, tuple(tab.shape), tuple(shape) + (3,)))
+    return tab
+
+
+def _same_space(src, space, what):
+    """A re-tabulation reads `src` through forward o backward of `space`: both must describe the same space."""
+    other = getattr(src, "space", None)
+    if other is None or not isinstance(other, atmosphere.Space):
+        return
+    if other.which != space.which or tuple(other.shape) != tuple(space.shape) or \
+            _lib.make_planet(other.planet).radius != _lib.make_planet(space.planet).radius or \
+            _lib.make_planet(other.planet).height != _lib.make_planet(space.planet).height:
+        raise TypeError("%s was tabulated over a different space (kind, shape or planet) than the one it is "
+                        "re-tabulated over" % what)
 
 
 def make_lookup_table(fun, space):
@@ -193,19 +211,21 @@ def make_lookup_table(fun, space):
                                                 src.kind, _lib.ptr(out), 0, 0, None))
         else:
             cfg = _config_for(shape4=shape, ray_steps=fun.steps)
-            dj = _table_of(src)
+            dj = _table_of(src, shape, "the point-scatter table")
             check(lib.atmlut_ray_scatter_table(C.byref(pl), sc, len(fun.scatter), C.byref(cfg), _lib.ptr(dj),
                                                _lib.ptr(out)))
         return out
     if isinstance(fun, PointScatter):
         e_tab = _table_of(fun.surface_radiance)
+        if e_tab.ndim != 3 or e_tab.shape[2] != 3:
+            raise TypeError("the surface-radiance table must have shape [height][sun elevation][3]")
         cfg = _config_for(shape4=shape, shape_e=e_tab.shape[:2], ray_steps=fun.ray_steps,
                           sphere_steps=fun.sphere_steps, intensity=fun.intensity)
         pl, sc = _lib.make_planet(fun.planet), _lib.make_scatter_array(fun.scatter)
         out = np.zeros(shape + (3,), np.float32)
         rs = fun.ray_scatter
-        a = _table_of(rs.a if isinstance(rs, MieCombined) else rs)
-        b = _table_of(rs.b) if isinstance(rs, MieCombined) else None
+        a = _table_of(rs.a if isinstance(rs, MieCombined) else rs, shape, "the ray-scatter table")
+        b = _table_of(rs.b, shape, "the Mie-strength table") if isinstance(rs, MieCombined) else None
         check(lib.atmlut_point_scatter_table(C.byref(pl), sc, len(fun.scatter), C.byref(cfg), _lib.ptr(a),
                                              _lib.ptr(b), rs.phase_component if isinstance(rs, MieCombined) else 0,
                                              _lib.ptr(e_tab), _lib.ptr(out)))
@@ -213,7 +233,9 @@ def make_lookup_table(fun, space):
     if isinstance(fun, SurfaceRadiance):
         rs = fun.ray_scatter
         a = _table_of(rs.a if isinstance(rs, MieCombined) else rs)
-        b = _table_of(rs.b) if isinstance(rs, MieCombined) else None
+        if a.ndim != 5 or a.shape[4] != 3:
+            raise TypeError("the ray-scatter table must have shape [height][elevation][sun elevation][heading][3]")
+        b = _table_of(rs.b, a.shape[:4], "the Mie-strength table") if isinstance(rs, MieCombined) else None
         cfg = _config_for(shape4=a.shape[:4], shape_e=shape, ray_steps=fun.steps)
         pl = _lib.make_planet(fun.planet)
         # surface-radiance takes no scatter argument (atmosphere.clj:225-230); the phase of MieCombined needs g
@@ -225,8 +247,11 @@ def make_lookup_table(fun, space):
         return out
     if isinstance(fun, (TableSum, InterpolationTable)) and isinstance(space, atmosphere.Space):
         ts = fun if isinstance(fun, TableSum) else TableSum(fun)
-        a = _table_of(ts.a) if ts.a is not None else None
-        b = _table_of(ts.b) if ts.b is not None else None
+        for name, part in (("the first table", ts.a), ("the second table", ts.b)):
+            if part is not None:
+                _same_space(part, space, name)
+        a = _table_of(ts.a, shape, "the first table") if ts.a is not None else None
+        b = _table_of(ts.b, shape, "the second table") if ts.b is not None else None
         kw = {0: "shape4", 1: "shape_e", 2: "shape_t"}[space.which]
         cfg = _config_for(**{kw: shape})
         pl = _lib.make_planet(space.planet)

@@ -54,3 +54,28 @@ def test_compose_space():
 def test_unknown_function_objects_are_rejected():
     with pytest.raises(TypeError):
         itp.make_lookup_table(42, itp.linear_space([0.0], [1.0], [3]))
+
+
+def test_tables_of_the_wrong_shape_are_refused_before_the_library_reads_them():
+    """The C entry points read prod(shape) * 3 floats from every table pointer: a mismatched table must never reach
+    them (it would be an out-of-bounds host read)."""
+    import numpy as np
+    import pytest
+    from sfsim_b200 import atmosphere, atmosphere_lut, interpolate as itp
+    earth = atmosphere_lut.earth
+    space4 = atmosphere.ray_scatter_space(earth, (4, 5, 3, 2))
+    small = itp.interpolation_table(np.zeros((2, 2, 2, 2, 3), np.float32), atmosphere.ray_scatter_space(earth, (2, 2, 2, 2)))
+    with pytest.raises(TypeError, match="shape"):
+        itp.make_lookup_table(itp.RayScatter(earth, [atmosphere_lut.mie, atmosphere_lut.rayleigh], 10, small), space4)
+    with pytest.raises(TypeError, match="different space"):
+        itp.make_lookup_table(small, space4)
+    other_planet = dict(earth, radius=1000.0, height=10.0)
+    same_shape = itp.interpolation_table(np.zeros((4, 5, 3, 2, 3), np.float32),
+                                         atmosphere.ray_scatter_space(other_planet, (4, 5, 3, 2)))
+    with pytest.raises(TypeError, match="different space"):
+        itp.make_lookup_table(same_shape, space4)
+    source = atmosphere.FirstOrder(atmosphere.FirstOrder.COMPONENT, earth, [atmosphere_lut.mie, atmosphere_lut.rayleigh],
+                                   atmosphere_lut.rayleigh, 10, (1, 1, 1))
+    with pytest.raises(TypeError, match="scatter"):
+        atmosphere.ray_scatter(earth, [atmosphere_lut.rayleigh, atmosphere_lut.mie], 10, source, (6378000.0, 0, 0),
+                               (1, 0, 0), (0, 1, 0), True)

@@ -1,12 +1,12 @@
 """Run under torchrun on N GPUs: the sharded build must produce exactly the bytes of a single-GPU build.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-        tools/multi_gpu_check.py [--configs reduced shipped stress] [--modes p2p nccl] [--log FILE]
+        tools/multi_gpu_check.py [--configs reduced shipped stress] [--modes p2p nccl] [--report FILE]
 
 For every (configuration, exchange mode): `--repeat` sharded builds in a row (buffer reuse across runs; the first
-captures the CUDA graph, the others replay it), then a kernel-by-kernel (eager) one; rank 0 downloads the four file
+captures the CUDA graph, the others replay it), then the timed variant of the build; rank 0 downloads the four file
 tables after each kind and compares them byte for byte with the tables of a single-GPU build made in the same process.
-One line per check, `MULTI_GPU_CHECK OK` at the end if all were identical; rank 0 appends the lines to --log.
+One line per check, `MULTI_GPU_CHECK OK` at the end if all were identical; rank 0 appends the lines to --report.
 """
 import argparse
 import hashlib
@@ -43,7 +43,7 @@ def main():
     ap.add_argument("--reduced", action="store_true", help="same as --configs reduced")
     ap.add_argument("--mode", default=None, help="same as --modes MODE")
     ap.add_argument("--repeat", type=int, default=3, help="builds in a row (exercises buffer reuse across runs)")
-    ap.add_argument("--log", default=None)
+    ap.add_argument("--report", default=None, help="append the result lines to this file")
     args = ap.parse_args()
     if args.reduced:
         args.configs = ["reduced"]
@@ -100,8 +100,8 @@ def main():
     if rank == 0:
         say("MULTI_GPU_CHECK %s world=%d configs=%s modes=%s" % ("OK" if ok else "FAILED", world, ",".join(args.configs),
                                                                  ",".join(args.modes)))
-        if args.log:
-            with open(args.log, "a") as f:
+        if args.report:
+            with open(args.report, "a") as f:
                 f.write("\n".join(lines) + "\n")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
