@@ -455,8 +455,8 @@ static int order_after(Builder &b, size_t &cursor, cudaStream_t from, cudaStream
 // dS and dE are double buffered so the side stream can still read order n-1 while order n is written.
 //
 // Peer-to-peer mode shards the side stream's kernels as well (surface radiance by texel, the S accumulation and the
-// file-layout tables by pair, the latter stored into rank 0's buffers only) and closes them with ONE side-stream
-// barrier per iteration.
+// file-layout tables by pair, the latter stored into rank 0's buffers only); the exchange after each point-scatter
+// closes them together with dJ, so all cross-GPU barriers stay on the main stream.
 static int builder_enqueue(Builder &b) {
   const Params &P = b.P;
   cudaStream_t st = b.main, side = b.side;
@@ -513,8 +513,6 @@ static int builder_enqueue(Builder &b) {
   const float4 *s_cur = b.R1;                                                         // :85     S_0
   const float4 *e_cur = nullptr;                                                      // :76     E_0 = 0
   std::vector<cudaEvent_t> side_done(N + 1, nullptr);   // side finished reading dS_n
-  std::vector<cudaEvent_t> de_ready(N + 1, nullptr);    // dE_n complete on this GPU
-  de_ready[0] = e_prepared;
 
   // S += dS (atmosphere_lut.clj:96-97): this rank's pairs into every GPU's copy, or the whole table
   auto accumulate_s = [&](const float4 *ds_tab) -> int {
@@ -538,7 +536,8 @@ static int builder_enqueue(Builder &b) {
 
   for (int it = 0; it < N; it++) {                                                    // :86
     char name[64];
-    // ---- side, order it: dE_{it+1} = surface-radiance(dS_it), E += dE, S += dS_it (all read dS_it)
+    // ---- side, order it: dE_{it+1} = surface-radiance(dS_it) and S += dS_it (both read dS_it; sharded in
+    // peer-to-peer mode: each rank stores its texels into every GPU's copy)
     TRY(order_after(b, ev, st, side));                                                // dS_it is complete
     if (it == 0) CUDA_TRY(cudaStreamWaitEvent(side, e_prepared, 0));
     float4 *de_next = debuf[(it + 1) & 1];
@@ -551,35 +550,36 @@ static int builder_enqueue(Builder &b) {
       TRY(file_table(b.M1, b.file_M, b.file_M_root));                                 // :101,105
     else
       TRY(accumulate_s(ds.tab_a));                                                    // :96-97
-    if (sharded_side) TRY(peer_barrier(b, 1, side));                                  // dE_{it+1} and S are whole
-    TRY(event_at(b, ev++, de_ready[it + 1]));
-    CUDA_TRY(cudaEventRecord(de_ready[it + 1], side));
-    LAUNCH(launch_resample_2d(P, 1, e_cur, de_next, b.Eacc_new, nullptr, side));      // :94-95
-    std::swap(b.Eacc, b.Eacc_new);
-    e_cur = b.Eacc;
     TRY(event_at(b, ev++, side_done[it]));
     CUDA_TRY(cudaEventRecord(side_done[it], side));
 
     // ---- main: dJ_{it+1} = point-scatter(dS_it, dE_it)
     snprintf(name, sizeof name, "iter%d_point_scatter", it + 1);
     TRY(stage_begin(b, name));
-    if (it == 0) CUDA_TRY(cudaStreamWaitEvent(st, e_prepared, 0));   // the per-direction constants come from the side stream
+    if (it == 0) CUDA_TRY(cudaStreamWaitEvent(st, e_prepared, 0));   // per-direction constants and dE_0 come from the side stream
     if (b.h_count > 0) {
       LAUNCH(launch_blend_dir_tiles(P, ds.tab_a, b.dir_info, b.n_sphere, b.h_first, b.h_stride, b.h_count, b.tiles_a, st));
       if (ds.tab_b)
         LAUNCH(launch_blend_dir_tiles(P, ds.tab_b, b.dir_info, b.n_sphere, b.h_first, b.h_stride, b.h_count, b.tiles_b, st));
     }
-    CUDA_TRY(cudaStreamWaitEvent(st, de_ready[it], 0));
+    // dE_it (it >= 1) was closed by the exchange after the previous point-scatter, on this stream
     LAUNCH(launch_point_scatter(P, shard, b.he_count, b.tiles_a, ds.tab_b ? b.tiles_b : nullptr, ds.phase_g,
                                 debuf[it & 1], b.sphere_dirs, b.sphere_w, b.n_sphere, b.dir_info, etab, b.peer_dJ, st));  // :88,90
-    // the next ray-scatter overwrites the buffer of dS_{it-1} (on every GPU in peer-to-peer mode): this
-    // rank's side stream must be done reading it before the exchange below lets anyone go on
-    if (it >= 1) CUDA_TRY(cudaStreamWaitEvent(st, side_done[it - 1], 0));
+    // The exchange below closes THREE things at once: dJ_{it+1}; the side stream's sharded dE_{it+1} and S (this
+    // rank's part is done once side_done[it] has fired, everybody's once the barrier is passed); and the
+    // permission to overwrite the buffer of dS_{it-1}, which the side streams of all ranks have finished reading.
+    // Every cross-GPU barrier thus sits on the main stream: no two barriers of one GPU are ever in flight together.
+    CUDA_TRY(cudaStreamWaitEvent(st, side_done[it], 0));
     TRY(stage_end(b));
     snprintf(name, sizeof name, "iter%d_point_scatter_exchange", it + 1);
     TRY(stage_begin(b, name));
     TRY(gather(b, b.dJ));
     TRY(stage_end(b));
+    // ---- side: E += dE_{it+1} needs the whole dE_{it+1}
+    TRY(order_after(b, ev, st, side));
+    LAUNCH(launch_resample_2d(P, 1, e_cur, de_next, b.Eacc_new, nullptr, side));      // :94-95
+    std::swap(b.Eacc, b.Eacc_new);
+    e_cur = b.Eacc;
 
     // ---- main: dS_{it+1} = ray-scatter(dJ_{it+1}) into the buffer that held dS_{it-1}
     snprintf(name, sizeof name, "iter%d_ray_scatter", it + 1);
@@ -595,7 +595,7 @@ static int builder_enqueue(Builder &b) {
     ds = SSource{ds_next, nullptr, 0.0};
   }
 
-  // ---- side: last accumulation and the file-layout tables; main joins
+  // ---- last accumulation and the file-layout tables (kernels on the side stream, barriers on the main stream)
   TRY(stage_begin(b, "final_accumulate_and_files"));
   TRY(order_after(b, ev, st, side));
   if (N == 0) {
@@ -605,12 +605,16 @@ static int builder_enqueue(Builder &b) {
     TRY(file_table(b.M1, b.file_M, b.file_M_root));                                   // :101,105
   } else {
     TRY(accumulate_s(ds.tab_a));                                                      // :96-97 (last order)
-    if (sharded_side) TRY(peer_barrier(b, 1, side));                                  // S is whole on every GPU
+    if (sharded_side) {
+      TRY(order_after(b, ev, side, st));
+      TRY(peer_barrier(b, 0, st));                                                    // S is whole on every GPU
+      TRY(order_after(b, ev, st, side));
+    }
   }
   LAUNCH(launch_resample_2d(P, 1, e_cur, nullptr, nullptr, b.file_E, side));          // :99,103
   TRY(file_table(s_cur, b.file_S, b.file_S_root));                                    // :100,104
-  if (sharded_side) TRY(peer_barrier(b, 1, side));                                    // rank 0 holds every pair's texels
   TRY(order_after(b, ev, side, st));
+  if (sharded_side) TRY(peer_barrier(b, 0, st));                                      // rank 0 holds every pair's texels
   TRY(stage_end(b));
   return 0;
 }
