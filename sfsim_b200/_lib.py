@@ -54,7 +54,7 @@ OPT_GRAPH, OPT_BARRIER_TIMEOUT_MS = 1, 2
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
-# every symbol include/sfsim_atmosphere.h declares
+# every symbol include/sfsim_atmosphere.h and include/sfsim_noise.h declare
 EXPORTS = [
     "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate", "atmlut_generate_multi",
@@ -73,6 +73,8 @@ EXPORTS = [
     "atmlut_index_forward_batch", "atmlut_index_backward_batch", "atmlut_index_map_batch",
     "atmlut_interpolate_batch",
     "atmlut_convert_4d_to_2d", "atmlut_write_floats", "atmlut_read_floats",
+    # include/sfsim_noise.h
+    "sfsim_worley_noise", "sfsim_perlin_noise", "sfsim_worley_distances", "sfsim_perlin_samples",
 ]
 
 _lib = None

@@ -1,4 +1,4 @@
-"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/sfsim_atmosphere.h declares,
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol the headers under include/ declare,
 its host-only helpers work, and the compute entry points fail loudly without a CUDA device (no fallback)."""
 import ctypes as C
 import os
@@ -15,9 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "sfsim_atmosphere.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(atmlut_\w+)\s*\(", text)))
+    """every function the headers under include/ declare (atmlut_* in sfsim_atmosphere.h, sfsim_* in sfsim_noise.h)"""
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b((?:atmlut|sfsim)_\w+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
