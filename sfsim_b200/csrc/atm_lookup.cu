@@ -529,8 +529,10 @@ __global__ void __launch_bounds__(256) k_ray_prepare(Params P, Shard shard, RayS
 //  * corner tiles stay in registers across samples (see k_ray_prepare); a cell change loads two new corners;
 //  * per-sample constants are 4 broadcast LDS.128 (a 128-bit broadcast costs two wavefronts), the offsets of the
 //    next sample are only fetched when its reload mask is not empty;
-//  * tile rows are padded by one entry when a row spans a multiple of 32 banks, so that texels of one quarter warp
-//    reading neighbouring rows at the same heading do not collide;
+//  * tile rows are NOT padded: the eight threads of a 128-bit shared-memory wavefront are the eight headings of one
+//    light-elevation row and read eight different columns, which unpadded rows of 8 x 16 bytes map to different
+//    banks whatever row each thread reads (measured: 4.97 wavefronts per LDS.128 against 5.46 with a pad entry;
+//    the excess over 4 comes from texels whose clamped headings share a column);
 //  * the exponent y and the scaled exponential come from one fused multiply-add each (table pre-multiplied by the
 //    coordinate scale, polynomial coefficients from the constant bank), floor / fraction from the 1.5 * 2^52
 //    rounding constant instead of conversion instructions.
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
   float4 *tiles = reinterpret_cast<float4 *>(s_exp + ((kExpTabSize + 1) & ~1));
   const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int ntex = S * A;
-  const int row_pitch = (A % 8 == 0) ? A + 1 : A;          // float4 entries per tile row
+  const int row_pitch = A;                                // float4 entries per tile row (see below: no padding)
   const int tile_entries = S * row_pitch;
   const int he = shard_pair(shard, blockIdx.x);
   const int h = he / E, e = he % E;
@@ -640,8 +642,9 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
 // ================================================================== K4, current version
 
 constexpr int kTileStages = 6;           // ring of direction tiles per CTA
-constexpr int kPointScatterThreads = 256;                         // consumer threads = texels per CTA
-constexpr int kPointScatterBlock = kPointScatterThreads + 32;     // plus one producer warp
+constexpr int kTileLead = 4;             // directions requested ahead of the one in work when there is no producer warp
+constexpr int kPointScatterThreads = 256;                         // consumer threads = texels per CTA (at most) ...
+constexpr int kPointScatterBlock = kPointScatterThreads + 32;     // ... plus one producer warp
 
 struct alignas(16) PointDir2 {
   double ox, oy;            // omega_d
@@ -672,8 +675,12 @@ __device__ __forceinline__ float4 blend4(float4 v00, float4 v01, float4 v10, flo
 // warps hand buffers back through "empty" mbarriers, so no warp ever waits for another one's arithmetic -- the
 // kernel is latency-bound (double-precision coordinate chains at 24 warps per SM), CTA-wide barriers per direction
 // cost more than anything else.
-template <bool kTwoTables, bool kDeShared>
-__global__ void __launch_bounds__(kPointScatterBlock, 3)
+// kProducerWarp = false is the variant for launches of at most one wave (the 508 pairs of an 8-GPU shard): thread 0
+// requests direction d + 4 before it works on direction d, and 64 registers keep four CTAs = 32 warps on an SM, so
+// that the whole launch is resident at once (three 288-thread CTAs per SM would need a second, nearly empty wave).
+// On a full grid it is the slower one (3.3 ms against 2.7 ms per build); both give the same bits.
+template <bool kTwoTables, bool kDeShared, bool kProducerWarp>
+__global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointScatterThreads, kProducerWarp ? 3 : 4)
     k_point_scatter(Params P, Shard shard, int chunks, int rows_max, const float4 *__restrict__ tiles_a,
                     const float4 *__restrict__ tiles_b, double phase_g, const float4 *__restrict__ de,
                     const double *__restrict__ dirs, const double *__restrict__ weights, int ndirs,
@@ -695,7 +702,8 @@ __global__ void __launch_bounds__(kPointScatterBlock, 3)
   const int chunk = blockIdx.x % chunks;
   const int h = he / E, e = he % E;
   const int tid = threadIdx.x;
-  const bool producer = tid >= kPointScatterThreads;
+  const int consumers = kPointScatterThreads;             // texels per CTA
+  const bool producer = kProducerWarp && tid >= consumers;
   if (tid == 0) {
     V3 x = index_to_height(P.planet, H, (double)h);
     V3 v;
@@ -708,32 +716,76 @@ __global__ void __launch_bounds__(kPointScatterBlock, 3)
     s_rows[1] = -1;
     for (int s = 0; s < kTileStages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kPointScatterThreads / 32);
+      mbar_init(&empty[s], consumers / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const double e_scale = sun_elevation_scale(Es);
-  for (int i = tid; i < kExpTabSize; i += blockDim.x) s_exp[i] = exp_table[i] * e_scale;   // see coord_from_exponent
-  if (kDeShared)
-    for (int i = tid; i < Eh * Es; i += blockDim.x) s_de[i] = ldg4(de + i);
   __syncthreads();
   const V3 x = v3(s_geom[0], 0.0, 0.0);
   const V3 v = v3(s_geom[1], s_geom[2], 0.0);
+  // this thread's texel: light direction and the sun-elevation rows of its lookups (the same for every direction)
+  const int texel = chunk * consumers + tid;
+  const bool active = !producer && texel < ntex;
+  const int si = active ? texel / A : 0, ai = active ? texel % A : 0;
+  const double ss = index_to_sin_sun_elevation(S, (double)si);
+  const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
+  const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
+  if (active) {
+    atomicMin(&s_rows[0], as.u);
+    atomicMax(&s_rows[1], as.v);
+  }
+  __syncthreads();
+  const int row_lo = s_rows[0];
+  const int nrows = min(s_rows[1] - row_lo + 1, rows_max);   // rows_max bounds it by construction (see the launcher)
+
+  // ---- the tiles stream into ring position d % kTileStages; the first requests go out before the per-direction
+  // constants below are worked out, so that their latency is not exposed at the head of the direction loop
+  const unsigned tile_bytes = (unsigned)(nrows * A) * (unsigned)sizeof(float4);
+  const size_t tile_first = (size_t)h * ndirs * ntex + (size_t)row_lo * A;   // float4 offset of direction 0's rows
+  auto request = [&](int d, int stage) {
+    const int use = d / kTileStages;
+    if (use > 0) mbar_wait(&empty[stage], (unsigned)(use - 1) & 1u);             // every consumer warp has released it
+    float4 *dst = stages + (size_t)stage * stage_texels;
+    mbar_expect_tx(&full[stage], kTwoTables ? 2 * tile_bytes : tile_bytes);
+    bulk_copy_g2s(dst, tiles_a + tile_first + (size_t)d * ntex, tile_bytes, &full[stage]);
+    if (kTwoTables) bulk_copy_g2s(dst + nrows * A, tiles_b + tile_first + (size_t)d * ntex, tile_bytes, &full[stage]);
+  };
+  if (producer) {
+    // producer warp: one lane runs up to kTileStages directions ahead of the slowest consumer warp
+    if (tid == consumers)
+      for (int d = 0; d < ndirs; d++) request(d, d % kTileStages);
+    return;
+  }
+  if (!kProducerWarp && tid == 0)
+    for (int d = 0; d < kTileLead && d < ndirs; d++) request(d, d);
+
+  // ---- per-direction constants, the exponential table and dE (consumer threads only from here on)
+  const double e_scale = sun_elevation_scale(Es);
+  for (int i = tid; i < kExpTabSize; i += consumers) s_exp[i] = exp_table[i] * e_scale;   // see coord_from_exponent
+  if (kDeShared)
+    for (int i = tid; i < Eh * Es; i += consumers) s_de[i] = ldg4(de + i);
   const double hx = height(P.planet, x);
-  for (int d = tid; d < ndirs; d += blockDim.x) {
+  // scattering (atmosphere.clj:42-47) = base * density: the density does not depend on the direction or the channel
+  double density[2] = {0.0, 0.0};
+  for (int c = 0; c < P.medium.n; c++) density[c] = exp(-(hx / P.medium.scale[c]));
+  for (int d = tid; d < ndirs; d += consumers) {
     const V3 omega = v3(dirs[3 * d], dirs[3 * d + 1], dirs[3 * d + 2]);
     const double mu = dot(v, omega);
     PointDir2 r;
     r.ox = omega.x;
     r.oy = omega.y;
     r.oz = omega.z;
-    // overall-in-scattering (atmosphere.clj:147-151); the phase function does not depend on the colour channel
+    // overall-in-scattering (atmosphere.clj:147-151).  phase (atmosphere.clj:56-61) with b^1.5 as b sqrt(b): one
+    // rounding more than pow, far below the float32 the sum is stored in, and a tenth of pow's instructions.
     double ph[2] = {0.0, 0.0};
-    for (int c = 0; c < P.medium.n; c++) ph[c] = phase(P.medium.g[c], mu);
+    for (int c = 0; c < P.medium.n; c++) {
+      const double g = P.medium.g[c], g2 = g * g, base = (1.0 + g2) - 2.0 * g * mu;
+      ph[c] = (3.0 * (1.0 - g2) * (1.0 + mu * mu)) / (8.0 * kPi * (2.0 + g2) * (base * sqrt(base)));
+    }
     for (int ch = 0; ch < 3; ch++) {
       double sum = 0.0;
       for (int c = 0; c < P.medium.n; c++) {
-        double term = scattering(P.medium, c, ch, hx) * ph[c];
+        double term = (P.medium.base[c][ch] * density[c]) * ph[c];
         sum = (c == 0) ? term : sum + term;
       }
       r.sc[ch] = (float)(sum * weights[d]);
@@ -756,37 +808,11 @@ __global__ void __launch_bounds__(kPointScatterBlock, 3)
     r.pad[0] = r.pad[1] = 0;
     pd[d] = r;
   }
-  // this thread's texel: light direction and the sun-elevation rows of its lookups (the same for every direction)
-  const int texel = chunk * kPointScatterThreads + tid;
-  const bool active = !producer && texel < ntex;
-  const int si = active ? texel / A : 0, ai = active ? texel % A : 0;
-  const double ss = index_to_sin_sun_elevation(S, (double)si);
-  const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
-  const Axis as = axis_from(sun_elevation_to_index(S, x, l), S);
-  if (active) {
-    atomicMin(&s_rows[0], as.u);
-    atomicMax(&s_rows[1], as.v);
-  }
-  __syncthreads();
-  const int row_lo = s_rows[0];
-  const int nrows = min(s_rows[1] - row_lo + 1, rows_max);   // rows_max bounds it by construction (see the launcher)
-
-  if (producer) {
-    // ---- producer warp: one lane streams the tiles, up to kTileStages directions ahead of the slowest consumer warp
-    if (tid == kPointScatterThreads) {
-      const unsigned tile_bytes = (unsigned)(nrows * A) * (unsigned)sizeof(float4);
-      const size_t tile_first = (size_t)h * ndirs * ntex + (size_t)row_lo * A;   // float4 offset of direction 0's rows
-      for (int d = 0; d < ndirs; d++) {
-        const int s = d % kTileStages, use = d / kTileStages;
-        if (use > 0) mbar_wait(&empty[s], (unsigned)(use - 1) & 1u);            // all consumer warps released it
-        float4 *dst = stages + (size_t)s * stage_texels;
-        mbar_expect_tx(&full[s], kTwoTables ? 2 * tile_bytes : tile_bytes);
-        bulk_copy_g2s(dst, tiles_a + tile_first + (size_t)d * ntex, tile_bytes, &full[s]);
-        if (kTwoTables) bulk_copy_g2s(dst + nrows * A, tiles_b + tile_first + (size_t)d * ntex, tile_bytes, &full[s]);
-      }
-    }
-    return;
-  }
+  // the consumer threads meet here (the producer warp is on its own way): named barrier 1
+  if (kProducerWarp)
+    asm volatile("bar.sync 1, %0;" ::"n"(kPointScatterThreads) : "memory");
+  else
+    __syncthreads();
 
   const float phase_c0 = (float)((3.0 * (1.0 - phase_g * phase_g)) / (8.0 * kPi * (2.0 + phase_g * phase_g)));
   const double a_half = 0.5 * (double)(A - 1);
@@ -802,6 +828,7 @@ __global__ void __launch_bounds__(kPointScatterBlock, 3)
     for (int j = 0; j < kTileStages; j++) {        // the ring position is the unrolled index: static addresses
       const int d = d0 + j;
       if (d >= ndirs) break;
+      if (!kProducerWarp && tid == 0 && d + kTileLead < ndirs) request(d + kTileLead, (j + kTileLead) % kTileStages);
       mbar_wait(&full[j], parity);
       if (active) {
         const float4 *tile = stages + (size_t)j * stage_texels;
@@ -883,7 +910,7 @@ static size_t ray_scatter_smem_v1(const Params &P) {
 
 static int ray_tile_entries(const Params &P) {
   const int S = P.shapes.s4[2], A = P.shapes.s4[3];
-  return S * ((A % 8 == 0) ? A + 1 : A);      // must match k_ray_scatter
+  return S * A;                               // must match k_ray_scatter
 }
 
 static size_t ray_scatter_smem_v2(const Params &P) {
@@ -947,17 +974,32 @@ cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const Dir
   return cudaGetLastError();
 }
 
-template <bool kTwoTables, bool kDeShared>
+template <bool kTwoTables, bool kDeShared, bool kProducerWarp>
 static cudaError_t launch_point_scatter_v2(const Params &P, Shard shard, int he_count, int chunks, int rows_max,
                                            size_t smem, const float4 *tiles_a, const float4 *tiles_b, double phase_g,
                                            const float4 *de, const double *dirs, const double *weights, int ndirs,
                                            const DirInfo *info, const double *exp_table, PeerOut out, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_point_scatter<kTwoTables, kDeShared>,
+  cudaError_t e = cudaFuncSetAttribute(k_point_scatter<kTwoTables, kDeShared, kProducerWarp>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_point_scatter<kTwoTables, kDeShared><<<he_count * chunks, kPointScatterBlock, smem, st>>>(
-      P, shard, chunks, rows_max, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out);
+  k_point_scatter<kTwoTables, kDeShared, kProducerWarp>
+      <<<he_count * chunks, kProducerWarp ? kPointScatterBlock : kPointScatterThreads, smem, st>>>(
+          P, shard, chunks, rows_max, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out);
   return cudaGetLastError();
+}
+
+template <bool kTwoTables, bool kDeShared>
+static cudaError_t launch_point_scatter_v2(bool producer_warp, const Params &P, Shard shard, int he_count, int chunks,
+                                           int rows_max, size_t smem, const float4 *tiles_a, const float4 *tiles_b,
+                                           double phase_g, const float4 *de, const double *dirs, const double *weights,
+                                           int ndirs, const DirInfo *info, const double *exp_table, PeerOut out,
+                                           cudaStream_t st) {
+  return producer_warp ? launch_point_scatter_v2<kTwoTables, kDeShared, true>(P, shard, he_count, chunks, rows_max, smem,
+                                                                              tiles_a, tiles_b, phase_g, de, dirs, weights,
+                                                                              ndirs, info, exp_table, out, st)
+                       : launch_point_scatter_v2<kTwoTables, kDeShared, false>(P, shard, he_count, chunks, rows_max, smem,
+                                                                               tiles_a, tiles_b, phase_g, de, dirs, weights,
+                                                                               ndirs, info, exp_table, out, st);
 }
 
 cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
@@ -972,6 +1014,11 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
     // more on either side (forward o backward moves that coordinate by < 1e-11), and the chunk may start mid-row
     const int chunks = (ntex + kPointScatterThreads - 1) / kPointScatterThreads;
     const int rows_max = std::min(S, (kPointScatterThreads + A - 1) / A + 3);
+    // a launch of at most one wave of four CTAs per SM runs without the producer warp (see the kernel)
+    static const int forced = env_variant("ATMLUT_K4_PRODUCER_WARP", -1);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool producer_warp = forced >= 0 ? forced != 0 : he_count * chunks > 4 * sms;
     const size_t ne = (size_t)P.shapes.se[0] * P.shapes.se[1];
     const size_t fixed = 128 + (size_t)ndirs * sizeof(PointDir2) + (size_t)((kExpTabSize + 1) & ~1) * sizeof(double);
     const size_t stages = (size_t)kTileStages * rows_max * A * sizeof(float4) * (tiles_b ? 2 : 1);
@@ -979,14 +1026,14 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
     const size_t smem = fixed + stages + (de_shared ? ne * sizeof(float4) : 0);
     if (smem <= 227 * 1024) {
       if (tiles_b)
-        return de_shared ? launch_point_scatter_v2<true, true>(P, shard, he_count, chunks, rows_max, smem, tiles_a, tiles_b,
-                                                               phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
-                         : launch_point_scatter_v2<true, false>(P, shard, he_count, chunks, rows_max, smem, tiles_a, tiles_b,
-                                                                phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
-      return de_shared ? launch_point_scatter_v2<false, true>(P, shard, he_count, chunks, rows_max, smem, tiles_a, tiles_b,
-                                                              phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
-                       : launch_point_scatter_v2<false, false>(P, shard, he_count, chunks, rows_max, smem, tiles_a, tiles_b,
-                                                               phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
+        return de_shared ? launch_point_scatter_v2<true, true>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                                                               tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
+                         : launch_point_scatter_v2<true, false>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                                                                tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
+      return de_shared ? launch_point_scatter_v2<false, true>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                                                              tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
+                       : launch_point_scatter_v2<false, false>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                                                               tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
     }
   }
   size_t smem = (size_t)ndirs * sizeof(PointDir);

@@ -138,7 +138,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
 template <int kPolyComp>
-__global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int kparts, int passes, int nchunks,
+__global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int he_count, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
                                                      unsigned long long *counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
   float *partial = reinterpret_cast<float *>(smem_raw + sizeof(ViewSmem));  // [6][blockDim] when kparts > 1
   const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int ntex = S * A;
-  const int he = shard_pair(shard, blockIdx.x / nchunks);
-  const int chunk = blockIdx.x % nchunks;
+  // The CTAs of a pair are dealt out chunk-major, the highest light-elevation rows first: those rows see the sun from
+  // most outer samples and cost the most, so the cheap CTAs are the ones that fill the tail of the launch.
+  const int he = shard_pair(shard, blockIdx.x % he_count);
+  const int chunk = nchunks - 1 - blockIdx.x / he_count;
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
@@ -492,11 +494,11 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
   static const int want_poly = env_int("ATMLUT_K3_POLY", 0);
   const int poly = want_poly ? P.fast.poly_exp : -1;
   if (poly == 1)
-    k_first_order<1><<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);
+    k_first_order<1><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
   else if (poly == 0)
-    k_first_order<0><<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);
+    k_first_order<0><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
   else
-    k_first_order<-1><<<he_count * nchunks, threads, smem, st>>>(P, shard, kparts, passes, nchunks, oa, ob, counter);
+    k_first_order<-1><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
   return cudaGetLastError();
 }
 
