@@ -238,7 +238,12 @@ def surface_radiance(planet, ray_scatter, steps, x, light_direction):
 # ------------------------------------------------------------------ interpolation spaces (atmosphere.clj:233-422)
 
 class Space:
-    """interpolation-space (interpolate.clj:22): shape + forward + backward, evaluated on the device."""
+    """interpolation-space (interpolate.clj:22): shape + forward + backward, evaluated on the device.
+
+    The reference's index maps take raw points: `height` subtracts the planet centre (sphere.clj:28-31) but
+    `is-above-horizon?` and the spaces assume the origin (atmosphere.clj:95-102).  The device maps subtract
+    `planet["centre"]` from every point first, which is the same thing for the only planets the tables are built for
+    (centre at the origin; the table builders refuse any other) and keeps the maps usable for a shifted planet."""
 
     def __init__(self, which, planet, shape):
         self.which, self.planet, self.shape = which, planet, tuple(int(s) for s in shape)

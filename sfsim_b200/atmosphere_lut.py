@@ -112,23 +112,11 @@ class AtmosphereLutBuilder:
         dist.barrier(group=process_group)
 
     def _install_allgather(self, process_group):
-        import torch
-        import torch.distributed as dist
-
-        class _Raw:
-            """__cuda_array_interface__ view of a raw device range, so torch can wrap the library's table."""
-
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False),
-                                                 "version": 3, "strides": None}
+        from . import sharding
 
         def allgather(_user, buf, bytes_per_rank, stream):
             try:
-                ext = torch.cuda.ExternalStream(stream)
-                with torch.cuda.stream(ext):
-                    full = torch.as_tensor(_Raw(buf, bytes_per_rank * self.world), device="cuda")
-                    mine = full[self.rank * (bytes_per_rank // 4):(self.rank + 1) * (bytes_per_rank // 4)]
-                    dist.all_gather_into_tensor(full, mine, group=process_group)
+                sharding.allgather_device_table(buf, bytes_per_rank, self.rank, self.world, stream, process_group)
                 self.gathers += 1
                 return 0
             except Exception as exc:  # surfaces as "allgather callback failed" from the library

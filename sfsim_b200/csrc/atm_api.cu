@@ -7,7 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sfsim_atmosphere.h"
+#include "sfsim_atmosphere.h"
 #include "atm_api_internal.h"
 #include "atm_tables.h"
 
@@ -91,17 +91,6 @@ int make_planet_medium(const atmlut_planet *planet, const atmlut_scatter *scatte
     P.fast.k[c] = (float)(-Rp * log2e / P.medium.scale[c]);
     P.fast.b[c] = (float)(delta * log2e / P.medium.scale[c]);
     for (int i = 0; i < 3; i++) P.fast.ext[c][i] = (float)(P.medium.base[c][i] / P.medium.quotient[c]);
-  }
-  // the hot sampler may take one component's exponentials from the FMA-pipe polynomial (ex2_poly2), which has no
-  // flush to zero: only a component whose exponent stays above -100 over the whole atmosphere qualifies
-  P.fast.poly_exp = -1;
-  for (int c = 1; c >= 0; c--) {
-    if (c >= n) continue;
-    const double min_exponent = -(Rt - Rp) * log2e / P.medium.scale[c];
-    if (P.fast.poly && min_exponent > -100.0) {
-      P.fast.poly_exp = c;
-      break;
-    }
   }
   for (int i = 0; i < 3; i++) P.intensity[i] = 1.0;
   return 0;

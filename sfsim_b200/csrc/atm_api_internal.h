@@ -5,7 +5,7 @@
 
 #include <cuda_runtime.h>
 
-#include "../../include/sfsim_atmosphere.h"
+#include "sfsim_atmosphere.h"
 #include "atm_device.cuh"
 
 namespace atm {

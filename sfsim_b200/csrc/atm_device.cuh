@@ -32,7 +32,6 @@ struct Fast {
   float k[2];        // -R' * log2(e) / scale_c     (exponent slope in units of h'/R')
   float b[2];        // delta * log2(e) / scale_c   (exponent offset)
   float ext[2][3];   // extinction at h = 0: base_c / quotient_c
-  int poly_exp;      // component whose exp2 the hot sampler may evaluate on the FMA pipe (exponent >= -100), or -1
 };
 
 struct Params {
@@ -125,46 +124,9 @@ __device__ __forceinline__ void densities_from_u2(const Fast &f, float2 u, float
   e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
 }
 
-// 2^a for TWO arguments on the FMA pipe (no MUFU): a = n + f with n = rint(a) taken with the 1.5 * 2^23 magic
-// constant, 2^f by a degree-6 polynomial on [-1/2, 1/2] (max relative error 9.5e-8 in float32, below MUFU.EX2's),
-// and n added to the exponent field with one integer shift-add.  Valid for a > -125 (no flush to zero here).
-// The hot sampler is bound by the MUFU pipe (16 / clk / SM) while the FMA pipe idles half of the time: moving one
-// in four exponentials here balances the two pipes.
-__device__ __forceinline__ float2 ex2_poly2(float2 a) {
-  const float magic = 12582912.0f;   // 1.5 * 2^23
-  const float2 t = __fadd2_rn(a, make_float2(magic, magic));
-  const float2 n = __fadd2_rn(t, make_float2(-magic, -magic));
-  const float2 f = __fadd2_rn(a, make_float2(-n.x, -n.y));
-  float2 p = __ffma2_rn(f, make_float2(0x1.41d332p-13f, 0x1.41d332p-13f), make_float2(0x1.5f456ap-10f, 0x1.5f456ap-10f));
-  p = __ffma2_rn(p, f, make_float2(0x1.3b2dbcp-7f, 0x1.3b2dbcp-7f));
-  p = __ffma2_rn(p, f, make_float2(0x1.c6aed4p-5f, 0x1.c6aed4p-5f));
-  p = __ffma2_rn(p, f, make_float2(0x1.ebfbdap-3f, 0x1.ebfbdap-3f));
-  p = __ffma2_rn(p, f, make_float2(0x1.62e430p-1f, 0x1.62e430p-1f));
-  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
-  // the low mantissa bits of t hold n (two's complement): shifting by 23 drops the magic constant's bits
-  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
-}
-
-// densities_from_u2 with the exponential of component `kPolyComp` evaluated by ex2_poly2
-template <int kPolyComp>
-__device__ __forceinline__ void densities_from_u2_poly(const Fast &f, float2 u, float2 &e0, float2 &e1) {
-  float2 q = __ffma2_rn(u, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
-  q = __ffma2_rn(q, u, make_float2(0.0625f, 0.0625f));
-  q = __ffma2_rn(q, u, make_float2(-0.125f, -0.125f));
-  q = __ffma2_rn(q, u, make_float2(0.5f, 0.5f));
-  const float2 hq = __fmul2_rn(u, q);  // h' / R'
-  const float2 a0 = __ffma2_rn(hq, make_float2(f.k[0], f.k[0]), make_float2(f.b[0], f.b[0]));
-  const float2 a1 = __ffma2_rn(hq, make_float2(f.k[1], f.k[1]), make_float2(f.b[1], f.b[1]));
-  e0 = kPolyComp == 0 ? ex2_poly2(a0) : make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-  e1 = kPolyComp == 1 ? ex2_poly2(a1) : make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
-}
-
 // Sequential variant (one thread per segment): u(m) advances by forward differences in double, two
 // samples per step (2 DADD per pair); the odd sample's u is the even one's float image plus the float
 // first difference.  Packed accumulators, two independent pairs in flight.
-// kPolyComp >= 0: the second pair of every 4-sample group takes that component's exponentials from ex2_poly2.
-template <int kPolyComp = -1>
 __device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
   if (P.fast.poly) {
     double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // u at m = 1/2
@@ -188,10 +150,7 @@ __device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q,
       step2 += step2_inc;
       d1f += d1f_inc;
       ue = trunc_d2f(u);
-      if (kPolyComp >= 0)
-        densities_from_u2_poly<kPolyComp>(P.fast, make_float2(ue, ue + d1f), e0, e1);
-      else
-        densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
+      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
       acc0b = __fadd2_rn(acc0b, e0);
       acc1b = __fadd2_rn(acc1b, e1);
       u += step2;

@@ -379,7 +379,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity))
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 28)) __trap();
 }
 
 
@@ -536,6 +536,9 @@ __global__ void __launch_bounds__(256) k_ray_prepare(Params P, Shard shard, RayS
 //  * the exponent y and the scaled exponential come from one fused multiply-add each (table pre-multiplied by the
 //    coordinate scale, polynomial coefficients from the constant bank), floor / fraction from the 1.5 * 2^52
 //    rounding constant instead of conversion instructions.
+//  * kSplitTile: the tile is kept as a float2 (red, green) plane and a float (blue) plane: a corner read is an LDS.64
+//    and an LDS.32 = 3 wavefronts instead of the 4 of an LDS.128 whose fourth lane is padding.
+template <bool kSplitTile>
 __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, const RaySample *__restrict__ samples,
                                                       const float4 *__restrict__ dj,
                                                       const double *__restrict__ exp_table, PeerOut out) {
@@ -547,8 +550,10 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
   float4 *tiles = reinterpret_cast<float4 *>(s_exp + ((kExpTabSize + 1) & ~1));
   const int E = P.shapes.s4[1], S = P.shapes.s4[2], A = P.shapes.s4[3];
   const int ntex = S * A;
-  const int row_pitch = A;                                // float4 entries per tile row (see below: no padding)
+  const int row_pitch = A;                                // entries per tile row (see below: no padding)
   const int tile_entries = S * row_pitch;
+  float2 *tiles_rg = reinterpret_cast<float2 *>(tiles);   // kSplitTile: [2][entries] float2, then [2][entries] float
+  float *tiles_b = reinterpret_cast<float *>(tiles_rg + 2 * tile_entries);
   const int he = shard_pair(shard, blockIdx.x);
   const int h = he / E, e = he % E;
   const int tid = threadIdx.x;
@@ -600,7 +605,12 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
       b.y = tr.y * fmaf(cw.w, c3.y, fmaf(cw.z, c2.y, fmaf(cw.y, c1.y, cw.x * c0.y)));
       b.z = tr.z * fmaf(cw.w, c3.z, fmaf(cw.z, c2.z, fmaf(cw.y, c1.z, cw.x * c0.z)));
       b.w = 0.0f;
-      tile[my_entry] = b;
+      if (kSplitTile) {
+        tiles_rg[(size_t)(k & 1) * tile_entries + my_entry] = make_float2(b.x, b.y);
+        tiles_b[(size_t)(k & 1) * tile_entries + my_entry] = b.z;
+      } else {
+        tile[my_entry] = b;
+      }
     }
     __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
     if (active) {
@@ -627,8 +637,22 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         fs.s = 0.0f;
       }
       const int sv = min(fs.u + 1, s_last);
-      const float4 *r0 = tile + fs.u * row_pitch, *r1 = tile + sv * row_pitch;
-      const float4 v00 = r0[aa.u], v01 = r0[aa.v], v10 = r1[aa.u], v11 = r1[aa.v];
+      float4 v00, v01, v10, v11;
+      if (kSplitTile) {
+        const float2 *g0 = tiles_rg + (size_t)(k & 1) * tile_entries + fs.u * row_pitch, *g1 = g0 + (sv - fs.u) * row_pitch;
+        const float *b0 = tiles_b + (size_t)(k & 1) * tile_entries + fs.u * row_pitch, *b1 = b0 + (sv - fs.u) * row_pitch;
+        const float2 a00 = g0[aa.u], a01 = g0[aa.v], a10 = g1[aa.u], a11 = g1[aa.v];
+        v00 = make_float4(a00.x, a00.y, b0[aa.u], 0.f);
+        v01 = make_float4(a01.x, a01.y, b0[aa.v], 0.f);
+        v10 = make_float4(a10.x, a10.y, b1[aa.u], 0.f);
+        v11 = make_float4(a11.x, a11.y, b1[aa.v], 0.f);
+      } else {
+        const float4 *r0 = tile + fs.u * row_pitch, *r1 = tile + sv * row_pitch;
+        v00 = r0[aa.u];
+        v01 = r0[aa.v];
+        v10 = r1[aa.u];
+        v11 = r1[aa.v];
+      }
       const float ws1 = fs.s, ws0 = 1.0f - fs.s;
       const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
       acc0 = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, fmaf(w00, v00.x, acc0))));
@@ -642,7 +666,6 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
 // ================================================================== K4, current version
 
 constexpr int kTileStages = 6;           // ring of direction tiles per CTA
-constexpr int kTileLead = 4;             // directions requested ahead of the one in work when there is no producer warp
 constexpr int kPointScatterThreads = 256;                         // consumer threads = texels per CTA (at most) ...
 constexpr int kPointScatterBlock = kPointScatterThreads + 32;     // ... plus one producer warp
 
@@ -675,12 +698,11 @@ __device__ __forceinline__ float4 blend4(float4 v00, float4 v01, float4 v10, flo
 // warps hand buffers back through "empty" mbarriers, so no warp ever waits for another one's arithmetic -- the
 // kernel is latency-bound (double-precision coordinate chains at 24 warps per SM), CTA-wide barriers per direction
 // cost more than anything else.
-// kProducerWarp = false is the variant for launches of at most one wave (the 508 pairs of an 8-GPU shard): thread 0
-// requests direction d + 4 before it works on direction d, and 64 registers keep four CTAs = 32 warps on an SM, so
-// that the whole launch is resident at once (three 288-thread CTAs per SM would need a second, nearly empty wave).
-// On a full grid it is the slower one (3.3 ms against 2.7 ms per build); both give the same bits.
-template <bool kTwoTables, bool kDeShared, bool kProducerWarp>
-__global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointScatterThreads, kProducerWarp ? 3 : 4)
+// (A variant without the producer warp -- thread 0 requesting four directions ahead, 64 registers, four CTAs per SM
+// so that the 508 CTAs of an 8-GPU shard are resident at once -- was measured slower everywhere: 3.3 ms against
+// 2.7 ms per build on one GPU, 0.73 ms against 0.67 ms on eight.)
+template <bool kTwoTables, bool kDeShared>
+__global__ void __launch_bounds__(kPointScatterBlock, 3)
     k_point_scatter(Params P, Shard shard, int chunks, int rows_max, const float4 *__restrict__ tiles_a,
                     const float4 *__restrict__ tiles_b, double phase_g, const float4 *__restrict__ de,
                     const double *__restrict__ dirs, const double *__restrict__ weights, int ndirs,
@@ -703,7 +725,7 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
   const int h = he / E, e = he % E;
   const int tid = threadIdx.x;
   const int consumers = kPointScatterThreads;             // texels per CTA
-  const bool producer = kProducerWarp && tid >= consumers;
+  const bool producer = tid >= consumers;
   if (tid == 0) {
     V3 x = index_to_height(P.planet, H, (double)h);
     V3 v;
@@ -716,7 +738,7 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
     s_rows[1] = -1;
     for (int s = 0; s < kTileStages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], consumers / 32);
+      mbar_init(&empty[s], consumers);          // every consumer thread releases a buffer itself
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -756,9 +778,6 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
       for (int d = 0; d < ndirs; d++) request(d, d % kTileStages);
     return;
   }
-  if (!kProducerWarp && tid == 0)
-    for (int d = 0; d < kTileLead && d < ndirs; d++) request(d, d);
-
   // ---- per-direction constants, the exponential table and dE (consumer threads only from here on)
   const double e_scale = sun_elevation_scale(Es);
   for (int i = tid; i < kExpTabSize; i += consumers) s_exp[i] = exp_table[i] * e_scale;   // see coord_from_exponent
@@ -809,10 +828,7 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
     pd[d] = r;
   }
   // the consumer threads meet here (the producer warp is on its own way): named barrier 1
-  if (kProducerWarp)
-    asm volatile("bar.sync 1, %0;" ::"n"(kPointScatterThreads) : "memory");
-  else
-    __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kPointScatterThreads) : "memory");
 
   const float phase_c0 = (float)((3.0 * (1.0 - phase_g * phase_g)) / (8.0 * kPi * (2.0 + phase_g * phase_g)));
   const double a_half = 0.5 * (double)(A - 1);
@@ -820,7 +836,6 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
   const float ws1 = as.s, ws0 = 1.0f - as.s;
   const int ru = (as.u - row_lo) * A, rv = (as.v - row_lo) * A;
   const double lx = l.x, ly = l.y, lz = l.z;
-  const int lane = tid & 31;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   for (int d0 = 0; d0 < ndirs; d0 += kTileStages) {
     const unsigned parity = (unsigned)(d0 / kTileStages) & 1u;
@@ -828,7 +843,6 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
     for (int j = 0; j < kTileStages; j++) {        // the ring position is the unrolled index: static addresses
       const int d = d0 + j;
       if (d >= ndirs) break;
-      if (!kProducerWarp && tid == 0 && d + kTileLead < ndirs) request(d + kTileLead, (j + kTileLead) % kTileStages);
       mbar_wait(&full[j], parity);
       if (active) {
         const float4 *tile = stages + (size_t)j * stage_texels;
@@ -884,8 +898,10 @@ __global__ void __launch_bounds__(kProducerWarp ? kPointScatterBlock : kPointSca
         acc1 = fmaf(r.sc[1], sv.y, acc1);
         acc2 = fmaf(r.sc[2], sv.z, acc2);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[j]);       // this warp is done with the buffer
+      // Every thread releases the buffer itself.  (One arrive per warp after __syncwarp() is correct as well, but
+      // measured 2 % slower, and compute-sanitizer's racecheck does not follow the ordering __syncwarp() gives the
+      // other lanes' reads: 4 reported hazards against 0 this way, profiles/r2/sanitizer_*.txt.)
+      mbar_arrive(&empty[j]);
     }
   }
   if (active) store_all(out, (size_t)he * ntex + texel, make_float4(acc0, acc1, acc2, 0.0f));
@@ -950,11 +966,15 @@ cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const
   const bool v2 = ray_scatter_uses_samples(P);
   const size_t smem = v2 ? ray_scatter_smem_v2(P) : ray_scatter_smem_v1(P);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;   // light-elevation x heading tile too large
-  cudaError_t e = v2 ? cudaFuncSetAttribute(k_ray_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                     : cudaFuncSetAttribute(k_ray_scatter_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const bool split = env_variant("ATMLUT_K6_SPLIT", 1) != 0;
+  cudaError_t e = !v2 ? cudaFuncSetAttribute(k_ray_scatter_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : split ? cudaFuncSetAttribute(k_ray_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(k_ray_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (v2)
-    k_ray_scatter<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, (const RaySample *)samples, dj, exp_table, out);
+  if (v2 && split)
+    k_ray_scatter<true><<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, (const RaySample *)samples, dj, exp_table, out);
+  else if (v2)
+    k_ray_scatter<false><<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, (const RaySample *)samples, dj, exp_table, out);
   else
     k_ray_scatter_v1<<<he_count, ray_scatter_threads(P), smem, st>>>(P, shard, dj, exp_table, out, counter);
   return cudaGetLastError();
@@ -974,32 +994,17 @@ cudaError_t launch_blend_dir_tiles(const Params &P, const float4 *tab, const Dir
   return cudaGetLastError();
 }
 
-template <bool kTwoTables, bool kDeShared, bool kProducerWarp>
+template <bool kTwoTables, bool kDeShared>
 static cudaError_t launch_point_scatter_v2(const Params &P, Shard shard, int he_count, int chunks, int rows_max,
                                            size_t smem, const float4 *tiles_a, const float4 *tiles_b, double phase_g,
                                            const float4 *de, const double *dirs, const double *weights, int ndirs,
                                            const DirInfo *info, const double *exp_table, PeerOut out, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_point_scatter<kTwoTables, kDeShared, kProducerWarp>,
+  cudaError_t e = cudaFuncSetAttribute(k_point_scatter<kTwoTables, kDeShared>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_point_scatter<kTwoTables, kDeShared, kProducerWarp>
-      <<<he_count * chunks, kProducerWarp ? kPointScatterBlock : kPointScatterThreads, smem, st>>>(
-          P, shard, chunks, rows_max, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out);
+  k_point_scatter<kTwoTables, kDeShared><<<he_count * chunks, kPointScatterBlock, smem, st>>>(
+      P, shard, chunks, rows_max, tiles_a, tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out);
   return cudaGetLastError();
-}
-
-template <bool kTwoTables, bool kDeShared>
-static cudaError_t launch_point_scatter_v2(bool producer_warp, const Params &P, Shard shard, int he_count, int chunks,
-                                           int rows_max, size_t smem, const float4 *tiles_a, const float4 *tiles_b,
-                                           double phase_g, const float4 *de, const double *dirs, const double *weights,
-                                           int ndirs, const DirInfo *info, const double *exp_table, PeerOut out,
-                                           cudaStream_t st) {
-  return producer_warp ? launch_point_scatter_v2<kTwoTables, kDeShared, true>(P, shard, he_count, chunks, rows_max, smem,
-                                                                              tiles_a, tiles_b, phase_g, de, dirs, weights,
-                                                                              ndirs, info, exp_table, out, st)
-                       : launch_point_scatter_v2<kTwoTables, kDeShared, false>(P, shard, he_count, chunks, rows_max, smem,
-                                                                               tiles_a, tiles_b, phase_g, de, dirs, weights,
-                                                                               ndirs, info, exp_table, out, st);
 }
 
 cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, const float4 *tiles_a,
@@ -1014,11 +1019,6 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
     // more on either side (forward o backward moves that coordinate by < 1e-11), and the chunk may start mid-row
     const int chunks = (ntex + kPointScatterThreads - 1) / kPointScatterThreads;
     const int rows_max = std::min(S, (kPointScatterThreads + A - 1) / A + 3);
-    // a launch of at most one wave of four CTAs per SM runs without the producer warp (see the kernel)
-    static const int forced = env_variant("ATMLUT_K4_PRODUCER_WARP", -1);
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool producer_warp = forced >= 0 ? forced != 0 : he_count * chunks > 4 * sms;
     const size_t ne = (size_t)P.shapes.se[0] * P.shapes.se[1];
     const size_t fixed = 128 + (size_t)ndirs * sizeof(PointDir2) + (size_t)((kExpTabSize + 1) & ~1) * sizeof(double);
     const size_t stages = (size_t)kTileStages * rows_max * A * sizeof(float4) * (tiles_b ? 2 : 1);
@@ -1026,13 +1026,13 @@ cudaError_t launch_point_scatter(const Params &P, Shard shard, int he_count, con
     const size_t smem = fixed + stages + (de_shared ? ne * sizeof(float4) : 0);
     if (smem <= 227 * 1024) {
       if (tiles_b)
-        return de_shared ? launch_point_scatter_v2<true, true>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+        return de_shared ? launch_point_scatter_v2<true, true>(P, shard, he_count, chunks, rows_max, smem, tiles_a,
                                                                tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
-                         : launch_point_scatter_v2<true, false>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                         : launch_point_scatter_v2<true, false>(P, shard, he_count, chunks, rows_max, smem, tiles_a,
                                                                 tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
-      return de_shared ? launch_point_scatter_v2<false, true>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+      return de_shared ? launch_point_scatter_v2<false, true>(P, shard, he_count, chunks, rows_max, smem, tiles_a,
                                                               tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st)
-                       : launch_point_scatter_v2<false, false>(producer_warp, P, shard, he_count, chunks, rows_max, smem, tiles_a,
+                       : launch_point_scatter_v2<false, false>(P, shard, he_count, chunks, rows_max, smem, tiles_a,
                                                                tiles_b, phase_g, de, dirs, weights, ndirs, info, exp_table, out, st);
     }
   }

@@ -65,7 +65,6 @@ __global__ void k_surface_radiance_base(Params P, float4 *out) {
 // acc_c[ch] = sum over outer samples k in [k0, k1) of
 //   exp(-h(p_k)/scale_c) T(x->p_k)[ch] T(p_k->sun)[ch] [sun visible from p_k]
 // for the texel with light direction l (atmosphere.clj:192-200 with the first-order sources :140-182).
-template <int kPolyComp>
 __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSmem &vs, V3 l, int k0, int k1, int kstride,
                                                   float acc0[3], float acc1[3], unsigned &esamples) {
   const int steps = P.shapes.ray_steps;
@@ -93,7 +92,7 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
     // transmittance p_k -> end point: samples p_k + (l t)(j + 1/2)/steps
     Quad q = make_quad(P.fast, rk2, pl * t, ll * t * t, steps);
     float s0, s1;
-    density_sums_seq<kPolyComp>(P, q, steps, s0, s1);
+    density_sums_seq(P, q, steps, s0, s1);
     esamples += steps;
     const float seg = (float)(t * llen * inv_steps);
     float tr[3];
@@ -137,7 +136,6 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
-template <int kPolyComp>
 __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int he_count, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
                                                      unsigned long long *counter) {
@@ -176,7 +174,7 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
       const double ss = index_to_sin_sun_elevation(S, (double)si);
       const V3 l = index_to_sun_direction(A, v, ss, (double)ai);
       float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
-      first_order_texel<kPolyComp>(P, vs, l, row_layout ? lane / A : 0, steps, kq, acc0, acc1, esamples);
+      first_order_texel(P, vs, l, row_layout ? lane / A : 0, steps, kq, acc0, acc1, esamples);
       if (kq > 1) {
         for (int o = A; o < 32; o <<= 1) {
 #pragma unroll
@@ -202,7 +200,7 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
       const double ss = index_to_sin_sun_elevation(S, (double)si);
       l = index_to_sun_direction(A, v, ss, (double)ai);
       const int k0 = (int)(((long long)steps * part) / kparts), k1 = (int)(((long long)steps * (part + 1)) / kparts);
-      first_order_texel<kPolyComp>(P, vs, l, k0, k1, 1, acc0, acc1, esamples);
+      first_order_texel(P, vs, l, k0, k1, 1, acc0, acc1, esamples);
     }
     __syncthreads();
 #pragma unroll
@@ -488,17 +486,7 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
     }
   }
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
-  // ATMLUT_K3_POLY=1: one exponential in four on the FMA pipe (ex2_poly2).  Measured on B200: 5.00 ms against 4.22 ms
-  // with all exponentials on the MUFU pipe -- packed FFMA2 halves the issue slots, not the FMA-pipe cycles, and
-  // that pipe is already 52 % busy -- so it is off by default and kept only for the comparison.
-  static const int want_poly = env_int("ATMLUT_K3_POLY", 0);
-  const int poly = want_poly ? P.fast.poly_exp : -1;
-  if (poly == 1)
-    k_first_order<1><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
-  else if (poly == 0)
-    k_first_order<0><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
-  else
-    k_first_order<-1><<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
+  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
   return cudaGetLastError();
 }
 

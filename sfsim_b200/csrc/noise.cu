@@ -4,7 +4,7 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/sfsim_noise.h"
+#include "sfsim_noise.h"
 #include "atm_api_internal.h"
 
 namespace atm {
