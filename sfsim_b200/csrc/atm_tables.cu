@@ -462,29 +462,35 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
                                unsigned long long *counter, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
-  static const int warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
+  static const int max_warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
   static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 4));
-  const int threads = warps * 32;
+  int warps = max_warps;
   const int ntex = P.shapes.s4[2] * P.shapes.s4[3];
   int kparts = 1, passes = 1, nchunks = 1;
-  if (ntex < threads) {
-    kparts = std::min(P.shapes.ray_steps, threads / ntex);
+  if (ntex < warps * 32) {
+    kparts = std::min(P.shapes.ray_steps, warps * 32 / ntex);
   } else {
     const int A = P.shapes.s4[3];
     const bool row_layout = A < 32 && (A & (A - 1)) == 0;     // must match the kernel
     const int ngroups = row_layout ? P.shapes.s4[2] : (ntex + 31) / 32;
     passes = std::min(want_passes, (ngroups + warps - 1) / warps);
-    // Small grids (one slab of a multi-GPU build, small tables): fewer row groups per warp, i.e. more and smaller
-    // CTAs per pair, until the launch spans several waves -- the repeated view-ray set-up (steps^2 samples per
-    // CTA) is cheaper than SMs idling behind the slowest CTA of a single wave.
+    // Small grids (one shard of a multi-GPU build, small tables): fewer row groups per warp, then fewer warps per
+    // CTA, i.e. more and smaller CTAs per pair, until the launch spans several waves -- the repeated view-ray
+    // set-up (steps^2 samples per CTA) is cheaper than SMs idling behind the last, expensive CTAs of a short launch.
     const int min_ctas = small_grid_ctas();
     for (;;) {
       const int total_warps = (ngroups + passes - 1) / passes;
       nchunks = (total_warps + warps - 1) / warps;
-      if ((long long)he_count * nchunks >= min_ctas || passes == 1) break;
-      passes = (passes + 1) / 2;
+      if ((long long)he_count * nchunks >= min_ctas) break;
+      if (passes > 1)
+        passes = (passes + 1) / 2;
+      else if (warps > 4)
+        warps /= 2;
+      else
+        break;
     }
   }
+  const int threads = warps * 32;
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
   k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
   return cudaGetLastError();
