@@ -1,8 +1,8 @@
 /*
  * 3-D noise textures of sfsim on the GPU -- part of libsfsim_atmosphere.so.
  *
- * Drop-in for the sampling loops of `clj -T:build worley` and `clj -T:build perlin` (build.clj:34-43 ->
- * src/clj/sfsim/worley.clj:95-112, src/clj/sfsim/perlin.clj:122-137).  The reference draws its random point /
+ * Drop-in for the sampling loops of `clj -T:build worley`, `perlin` and `bluenoise` (build.clj:34-51 ->
+ * src/clj/sfsim/worley.clj:95-112, src/clj/sfsim/perlin.clj:122-137, src/clj/sfsim/bluenoise.clj:175-185).  The reference draws its random point /
  * gradient grid with clojure.core/rand inside those functions; here the grid is an INPUT, so a host that wants the
  * reference's exact texture passes the grid it drew (the reference's own tests rebind random-point-grid and
  * random-gradient-grid the same way, t_worley.clj:70-74, t_perlin.clj:140-146).  All arithmetic is IEEE double in
@@ -31,6 +31,15 @@ int sfsim_perlin_noise(const double *gradients, int divisions, int size, float *
 /* the un-normalised samples (closest distances / Perlin sums) in double, for parity checks */
 int sfsim_worley_distances(const double *grid, int divisions, int size, double *out);
 int sfsim_perlin_samples(const double *gradients, int divisions, int size, double *out);
+
+/* blue-noise (bluenoise.clj:175-185), the void-and-cluster dither array of `clj -T:build bluenoise` (build.clj:45-51).
+ * picks: the n distinct indices pick-n (bluenoise.clj:35-40) drew from 0 .. size^2 - 1; ftab: the density function
+ * over the wrapped offsets, ftab[(dy + size/2) * size + (dx + size/2)] = f(dx, dy) (density-function :53-56);
+ * dither: int[size^2], every rank 0 .. size^2 - 1 exactly once.  The insertions are serial (each needs the arg-max or
+ * arg-min of the density array the previous one left behind); each of them runs on 1024 threads of one CTA. */
+int sfsim_blue_noise(const int *picks, int n, int size, const double *ftab, int *dither);
+/* the float array build.clj:45-51 writes: dither / size / size, with density-function(sigma) tabulated by the host */
+int sfsim_blue_noise_texture(const int *picks, int n, int size, double sigma, float *out);
 
 #ifdef __cplusplus
 }

@@ -77,3 +77,97 @@ def perlin_noise(gradients, size):
     out = np.zeros(size ** 3)
     lib().orc_perlin_noise(_dp(g), C.c_long(g.shape[0]), C.c_long(size), _dp(out))
     return out
+
+
+# ------------------------------------------------------------------ blue noise (bluenoise.clj)
+
+c_long_p = C.POINTER(C.c_long)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+
+def density_table(m, f):
+    """ftab[(dy + m//2) * m + (dx + m//2)] = f(dx, dy) over the offsets `wrap` can return"""
+    off = m // 2
+    return np.array([[float(f(dx - off, dy - off)) for dx in range(m)] for dy in range(m)], dtype=np.float64)
+
+
+def density_function(sigma):
+    """bluenoise.clj:53-56"""
+    import math
+    return lambda dx, dy: math.exp(-((dx * dx + dy * dy) / (2.0 * sigma * sigma)))
+
+
+def wrap(x, m):
+    lib().orc_wrap.restype = C.c_long
+    return lib().orc_wrap(C.c_long(x), C.c_long(m))
+
+
+def _mask(mask):
+    return np.ascontiguousarray(np.asarray(mask, dtype=bool).astype(np.uint8))
+
+
+def argmax_with_mask(arr, mask):
+    a, k = np.ascontiguousarray(arr, dtype=np.float64), _mask(mask)
+    lib().orc_argmax_with_mask.restype = C.c_long
+    return lib().orc_argmax_with_mask(_dp(a), k.ctypes.data_as(c_ubyte_p), C.c_long(len(a)))
+
+
+def argmin_with_mask(arr, mask):
+    a, k = np.ascontiguousarray(arr, dtype=np.float64), _mask(mask)
+    lib().orc_argmin_with_mask.restype = C.c_long
+    return lib().orc_argmin_with_mask(_dp(a), k.ctypes.data_as(c_ubyte_p), C.c_long(len(a)))
+
+
+def density_sample(mask, m, f, cx, cy):
+    k, t = _mask(mask), density_table(m, f)
+    lib().orc_density_sample.restype = C.c_double
+    return lib().orc_density_sample(k.ctypes.data_as(c_ubyte_p), C.c_long(m), _dp(t), C.c_long(cx), C.c_long(cy))
+
+
+def density_array(mask, m, f):
+    k, t = _mask(mask), density_table(m, f)
+    out = np.zeros(m * m)
+    lib().orc_density_array(k.ctypes.data_as(c_ubyte_p), C.c_long(m), _dp(t), _dp(out))
+    return out
+
+
+def density_change(density, m, sign, f, index):
+    d, t = np.array(density, dtype=np.float64), density_table(m, f)
+    lib().orc_density_change(_dp(d), C.c_long(m), C.c_int(sign), _dp(t), C.c_long(index))
+    return d
+
+
+def seed_pattern(mask, m, f):
+    k, t = _mask(mask).copy(), density_table(m, f)
+    lib().orc_seed_pattern(k.ctypes.data_as(c_ubyte_p), C.c_long(m), _dp(t))
+    return k.astype(bool)
+
+
+def dither_phase1(mask, m, n, f):
+    k, t = _mask(mask), density_table(m, f)
+    dither = np.zeros(m * m, dtype=np.int64)
+    lib().orc_dither_phase1(k.ctypes.data_as(c_ubyte_p), C.c_long(m), C.c_long(n), _dp(t), dither.ctypes.data_as(c_long_p))
+    return dither
+
+
+def dither_phase2(mask, m, n, dither, f):
+    k, t = _mask(mask).copy(), density_table(m, f)
+    d = np.array(dither, dtype=np.int64)
+    lib().orc_dither_phase2(k.ctypes.data_as(c_ubyte_p), C.c_long(m), C.c_long(n), d.ctypes.data_as(c_long_p), _dp(t))
+    return d, k.astype(bool)
+
+
+def dither_phase3(mask, m, n, dither, f):
+    k, t = _mask(mask), density_table(m, f)
+    d = np.array(dither, dtype=np.int64)
+    lib().orc_dither_phase3(k.ctypes.data_as(c_ubyte_p), C.c_long(m), C.c_long(n), d.ctypes.data_as(c_long_p), _dp(t))
+    return d
+
+
+def blue_noise(m, picks, sigma=None, table=None):
+    """bluenoise.clj:175-185 with the seed picks given; returns the dither array (int64[m*m])"""
+    t = np.ascontiguousarray(table, dtype=np.float64) if table is not None else density_table(m, density_function(sigma))
+    p = np.ascontiguousarray(picks, dtype=np.int64)
+    dither = np.zeros(m * m, dtype=np.int64)
+    lib().orc_blue_noise(C.c_long(m), C.c_long(len(p)), p.ctypes.data_as(c_long_p), _dp(t), dither.ctypes.data_as(c_long_p))
+    return dither

@@ -113,3 +113,149 @@ void orc_perlin_noise(const double *gradients, long divisions, long size, double
       }
   for (long t = 0; t < n; t++) out[t] = (out[t] - minimum) / (maximum - minimum);
 }
+
+/* ------------------------------------------------------------------ blue noise (bluenoise.clj), void-and-cluster
+ *
+ * The density function f(dx, dy) = exp(-(dx^2 + dy^2) / (2 sigma^2)) (bluenoise.clj:53-56) is passed as a TABLE
+ * ftab[(dy + m/2) * m + (dx + m/2)] over the wrapped offsets, and the random seed picks (pick-n, :35-40) as a list,
+ * so that an implementation can be compared decision for decision: everything else is additions, subtractions and
+ * comparisons of doubles. */
+
+/* bluenoise.clj:73-78 wrap */
+long orc_wrap(long x, long m) {
+  long offset = m / 2;
+  long r = (x + offset) % m;
+  if (r < 0) r += m;
+  return r - offset;
+}
+
+static double ftab_at(const double *ftab, long m, long dx, long dy) {
+  long offset = m / 2;
+  return ftab[(orc_wrap(dy, m) + offset) * m + (orc_wrap(dx, m) + offset)];
+}
+
+/* bluenoise.clj:59-63 argmax-with-mask: largest element whose mask is true; max-key keeps the LAST of equal maxima */
+long orc_argmax_with_mask(const double *arr, const unsigned char *mask, long count) {
+  long best = -1;
+  for (long i = 0; i < count; i++)
+    if (mask[i] && (best < 0 || arr[i] >= arr[best])) best = i;
+  return best;
+}
+
+/* bluenoise.clj:66-70 argmin-with-mask: smallest element whose mask is false; min-key keeps the LAST of equal minima */
+long orc_argmin_with_mask(const double *arr, const unsigned char *mask, long count) {
+  long best = -1;
+  for (long i = 0; i < count; i++)
+    if (!mask[i] && (best < 0 || arr[i] <= arr[best])) best = i;
+  return best;
+}
+
+/* bluenoise.clj:81-91 density-sample: sum in (y, x) order over the set mask entries */
+double orc_density_sample(const unsigned char *mask, long m, const double *ftab, long cx, long cy) {
+  double sum = 0.0;
+  for (long y = 0; y < m; y++)
+    for (long x = 0; x < m; x++)
+      sum = sum + (mask[y * m + x] ? ftab_at(ftab, m, x - cx, y - cy) : 0.0);
+  return sum;
+}
+
+/* bluenoise.clj:94-98 density-array */
+void orc_density_array(const unsigned char *mask, long m, const double *ftab, double *out) {
+  for (long cy = 0; cy < m; cy++)
+    for (long cx = 0; cx < m; cx++) out[cy * m + cx] = orc_density_sample(mask, m, ftab, cx, cy);
+}
+
+/* bluenoise.clj:101-111 density-change, in place; sign = +1 / -1 for the reference's `+` / `-` */
+void orc_density_change(double *density, long m, int sign, const double *ftab, long index) {
+  long cy = index / m, cx = index % m;
+  for (long y = 0; y < m; y++)
+    for (long x = 0; x < m; x++) {
+      double f = ftab_at(ftab, m, x - cx, y - cy);
+      density[y * m + x] = sign > 0 ? density[y * m + x] + f : density[y * m + x] - f;
+    }
+}
+
+/* bluenoise.clj:114-126 seed-pattern (mask modified in place) */
+void orc_seed_pattern(unsigned char *mask, long m, const double *ftab) {
+  double *density = (double *)malloc((size_t)(m * m) * sizeof(double));
+  orc_density_array(mask, m, ftab, density);
+  for (;;) {
+    long cluster = orc_argmax_with_mask(density, mask, m * m);
+    mask[cluster] = 0;
+    orc_density_change(density, m, -1, ftab, cluster);
+    long hole = orc_argmin_with_mask(density, mask, m * m);
+    mask[hole] = 1;
+    if (cluster == hole) break;
+    orc_density_change(density, m, +1, ftab, hole);
+  }
+  free(density);
+}
+
+/* bluenoise.clj:129-143 dither-phase1: mask is NOT modified for the caller (the reference's is immutable) */
+void orc_dither_phase1(const unsigned char *mask_in, long m, long n, const double *ftab, long *dither) {
+  long count = m * m;
+  unsigned char *mask = (unsigned char *)malloc((size_t)count);
+  double *density = (double *)malloc((size_t)count * sizeof(double));
+  for (long i = 0; i < count; i++) {
+    mask[i] = mask_in[i];
+    dither[i] = 0;
+  }
+  orc_density_array(mask, m, ftab, density);
+  while (n > 0) {
+    long cluster = orc_argmax_with_mask(density, mask, count);
+    orc_density_change(density, m, -1, ftab, cluster);
+    mask[cluster] = 0;
+    n--;
+    dither[cluster] = n;
+  }
+  free(mask);
+  free(density);
+}
+
+/* bluenoise.clj:146-156 dither-phase2: fills the mask (in place) until half of it is set */
+void orc_dither_phase2(unsigned char *mask, long m, long n, long *dither, const double *ftab) {
+  long count = m * m;
+  double *density = (double *)malloc((size_t)count * sizeof(double));
+  orc_density_array(mask, m, ftab, density);
+  while (n < count / 2) {
+    long hole = orc_argmin_with_mask(density, mask, count);
+    orc_density_change(density, m, +1, ftab, hole);
+    mask[hole] = 1;
+    dither[hole] = n;
+    n++;
+  }
+  free(density);
+}
+
+/* bluenoise.clj:159-172 dither-phase3 */
+void orc_dither_phase3(const unsigned char *mask, long m, long n, long *dither, const double *ftab) {
+  long count = m * m;
+  unsigned char *mask_not = (unsigned char *)malloc((size_t)count);
+  double *density = (double *)malloc((size_t)count * sizeof(double));
+  for (long i = 0; i < count; i++) mask_not[i] = !mask[i];
+  orc_density_array(mask_not, m, ftab, density);
+  while (n < count) {
+    long cluster = orc_argmax_with_mask(density, mask_not, count);
+    orc_density_change(density, m, -1, ftab, cluster);
+    mask_not[cluster] = 0;
+    dither[cluster] = n;
+    n++;
+  }
+  free(mask_not);
+  free(density);
+}
+
+/* bluenoise.clj:175-185 blue-noise: picks = the n indices pick-n drew */
+void orc_blue_noise(long m, long n, const long *picks, const double *ftab, long *dither) {
+  long count = m * m;
+  unsigned char *seed = (unsigned char *)calloc((size_t)count, 1);
+  for (long i = 0; i < n; i++) seed[picks[i]] = 1;               /* scatter-mask :46-49 */
+  orc_seed_pattern(seed, m, ftab);
+  orc_dither_phase1(seed, m, n, ftab, dither);
+  unsigned char *half = (unsigned char *)malloc((size_t)count);
+  for (long i = 0; i < count; i++) half[i] = seed[i];
+  orc_dither_phase2(half, m, n, dither, ftab);
+  orc_dither_phase3(half, m, count / 2, dither, ftab);
+  free(seed);
+  free(half);
+}

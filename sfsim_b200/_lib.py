@@ -75,6 +75,7 @@ EXPORTS = [
     "atmlut_convert_4d_to_2d", "atmlut_write_floats", "atmlut_read_floats",
     # include/sfsim_noise.h
     "sfsim_worley_noise", "sfsim_perlin_noise", "sfsim_worley_distances", "sfsim_perlin_samples",
+    "sfsim_blue_noise", "sfsim_blue_noise_texture",
 ]
 
 _lib = None

@@ -1,8 +1,10 @@
 // 3-D Worley and Perlin noise textures (include/sfsim_noise.h): one thread per texture sample, double precision in
 // the reference's operation order (the translation unit is compiled with -fmad=false), a device-wide min / max by
 // atomics on order-preserving integer keys, and a second pass that normalises and casts to float32.
+#include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "sfsim_noise.h"
 #include "atm_api_internal.h"
@@ -148,6 +150,175 @@ __global__ void k_perlin_finish(const double *__restrict__ raw, long long n, con
   out[t] = (float)((raw[t] - minimum) / (maximum - minimum));
 }
 
+// ------------------------------------------------------------------ blue noise (bluenoise.clj), void-and-cluster
+//
+// 4096 insertions at the shipped size 64 x 64, each an arg-max / arg-min over the whole density array followed by an
+// update of the whole array: parallel inside a step (one element per thread and trip), strictly serial across steps.
+// One persistent CTA of 1024 threads runs all phases; the density function arrives as a table over the wrapped
+// offsets (host libm exp), so that every decision can be checked against a CPU restatement: everything here is additions,
+// subtractions and comparisons of doubles in the reference's order.
+
+struct BlueNoise {
+  int m, n;
+  const double *ftab;        // [(dy + m/2) * m + (dx + m/2)]
+  double *density;           // [m * m]
+  unsigned char *mask;       // seed pattern, then the half-filled mask
+  unsigned char *work;       // working copy (phase 1) / negated mask (phase 3)
+  int *dither;
+};
+
+// bluenoise.clj:73-78 wrap
+__device__ __forceinline__ int blue_wrap(int x, int m) {
+  const int offset = m / 2;
+  int r = (x + offset) % m;
+  if (r < 0) r += m;
+  return r - offset;
+}
+
+// bluenoise.clj:94-98 density-array: every element the (y, x)-ordered sum over the set mask entries (:81-91)
+__device__ void blue_density_array(const BlueNoise &b, const unsigned char *mask) {
+  const int m = b.m, count = m * m, offset = m / 2;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int cy = i / m, cx = i % m;
+    double sum = 0.0;
+    for (int y = 0; y < m; y++) {
+      const int wy = (blue_wrap(y - cy, m) + offset) * m;
+      for (int x = 0; x < m; x++)
+        sum = sum + (mask[y * m + x] ? b.ftab[wy + blue_wrap(x - cx, m) + offset] : 0.0);
+    }
+    b.density[i] = sum;
+  }
+  __syncthreads();
+}
+
+// bluenoise.clj:101-111 density-change
+__device__ void blue_density_change(const BlueNoise &b, int sign, int index) {
+  const int m = b.m, count = m * m, offset = m / 2;
+  const int cy = index / m, cx = index % m;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int y = i / m, x = i % m;
+    const double f = b.ftab[(blue_wrap(y - cy, m) + offset) * m + blue_wrap(x - cx, m) + offset];
+    b.density[i] = sign > 0 ? b.density[i] + f : b.density[i] - f;
+  }
+  __syncthreads();
+}
+
+// argmax-with-mask (want_max, entries whose mask is true) / argmin-with-mask (entries whose mask is false),
+// bluenoise.clj:59-70.  max-key / min-key keep the LAST of equal extrema: ties go to the larger index.
+__device__ int blue_arg_extreme(const BlueNoise &b, const unsigned char *mask, bool want_max) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_result;
+  const int count = b.m * b.m;
+  double best = 0.0;
+  int best_i = -1;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    if ((mask[i] != 0) != want_max) continue;
+    const double v = b.density[i];
+    if (best_i < 0 || (want_max ? v >= best : v <= best)) {
+      best = v;
+      best_i = i;
+    }
+  }
+  auto better = [&](double v, int i, double w, int j) {   // is (v, i) preferred over (w, j)?
+    if (i < 0) return false;
+    if (j < 0) return true;
+    if (v != w) return want_max ? v > w : v < w;
+    return i > j;
+  };
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (better(v, i, best, best_i)) {
+      best = v;
+      best_i = i;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_val[warp] = best;
+    s_idx[warp] = best_i;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nwarps = blockDim.x >> 5;
+    best = lane < nwarps ? s_val[lane] : 0.0;
+    best_i = lane < nwarps ? s_idx[lane] : -1;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double v = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (better(v, i, best, best_i)) {
+        best = v;
+        best_i = i;
+      }
+    }
+    if (lane == 0) s_result = best_i;
+  }
+  __syncthreads();
+  const int result = s_result;
+  __syncthreads();          // s_result is reused by the next call
+  return result;
+}
+
+// blue-noise, bluenoise.clj:175-185; the mask arrives with the seed picks scattered (scatter-mask :46-49)
+__global__ void __launch_bounds__(1024) k_blue_noise(BlueNoise b) {
+  const int count = b.m * b.m;
+  // ---- seed-pattern (:114-126)
+  blue_density_array(b, b.mask);
+  for (;;) {
+    const int cluster = blue_arg_extreme(b, b.mask, true);
+    if (threadIdx.x == 0) b.mask[cluster] = 0;
+    __syncthreads();
+    blue_density_change(b, -1, cluster);
+    const int hole = blue_arg_extreme(b, b.mask, false);
+    if (threadIdx.x == 0) b.mask[hole] = 1;
+    __syncthreads();
+    if (cluster == hole) break;
+    blue_density_change(b, +1, hole);
+  }
+  // ---- phase 1 (:129-143): remove the seed samples one by one, densest first
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    b.work[i] = b.mask[i];
+    b.dither[i] = 0;
+  }
+  __syncthreads();
+  blue_density_array(b, b.work);
+  for (int n = b.n; n > 0;) {
+    const int cluster = blue_arg_extreme(b, b.work, true);
+    blue_density_change(b, -1, cluster);
+    n--;
+    if (threadIdx.x == 0) {
+      b.work[cluster] = 0;
+      b.dither[cluster] = n;
+    }
+    __syncthreads();
+  }
+  // ---- phase 2 (:146-156): fill the largest voids until half of the mask is set
+  blue_density_array(b, b.mask);
+  for (int n = b.n; n < count / 2; n++) {
+    const int hole = blue_arg_extreme(b, b.mask, false);
+    blue_density_change(b, +1, hole);
+    if (threadIdx.x == 0) {
+      b.mask[hole] = 1;
+      b.dither[hole] = n;
+    }
+    __syncthreads();
+  }
+  // ---- phase 3 (:159-172): negate the mask and remove its clusters
+  for (int i = threadIdx.x; i < count; i += blockDim.x) b.work[i] = !b.mask[i];
+  __syncthreads();
+  blue_density_array(b, b.work);
+  for (int n = count / 2; n < count; n++) {
+    const int cluster = blue_arg_extreme(b, b.work, true);
+    blue_density_change(b, -1, cluster);
+    if (threadIdx.x == 0) {
+      b.work[cluster] = 0;
+      b.dither[cluster] = n;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ host
 
 namespace {
@@ -220,4 +391,72 @@ extern "C" int sfsim_worley_distances(const double *grid, int divisions, int siz
 
 extern "C" int sfsim_perlin_samples(const double *gradients, int divisions, int size, double *out) {
   return atm::run_noise(1, gradients, divisions, size, nullptr, out);
+}
+
+namespace atm {
+namespace {
+
+struct BlueBuffers {
+  double *ftab = nullptr, *density = nullptr;
+  unsigned char *mask = nullptr, *work = nullptr;
+  int *dither = nullptr;
+  ~BlueBuffers() {
+    cudaFree(ftab);
+    cudaFree(density);
+    cudaFree(mask);
+    cudaFree(work);
+    cudaFree(dither);
+  }
+};
+
+int run_blue_noise(const int *picks, int n, int m, const double *ftab, int *dither) {
+  if (ensure_init()) return 1;
+  if (!picks || !ftab || !dither) return fail("picks, ftab and dither must not be NULL");
+  if (m < 2 || m > 1024) return fail("the dither array size must be in [2, 1024]");
+  const int count = m * m;
+  if (n < 1 || n > count / 2) return fail("the number of seed samples must be in [1, size^2 / 2]");
+  std::vector<unsigned char> mask((size_t)count, 0);
+  for (int i = 0; i < n; i++) {
+    if (picks[i] < 0 || picks[i] >= count) return fail("seed index out of range");
+    if (mask[picks[i]]) return fail("seed indices must be distinct (pick-n draws without replacement)");
+    mask[picks[i]] = 1;                                  // scatter-mask, bluenoise.clj:46-49
+  }
+  cudaStream_t st = stream();
+  BlueBuffers b;
+  CUDA_TRY(cudaMalloc((void **)&b.ftab, (size_t)count * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&b.density, (size_t)count * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void **)&b.mask, (size_t)count));
+  CUDA_TRY(cudaMalloc((void **)&b.work, (size_t)count));
+  CUDA_TRY(cudaMalloc((void **)&b.dither, (size_t)count * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(b.ftab, ftab, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b.mask, mask.data(), (size_t)count, cudaMemcpyHostToDevice, st));
+  BlueNoise args = {m, n, b.ftab, b.density, b.mask, b.work, b.dither};
+  k_blue_noise<<<1, 1024, 0, st>>>(args);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(dither, b.dither, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // namespace
+}  // namespace atm
+
+extern "C" int sfsim_blue_noise(const int *picks, int n, int size, const double *ftab, int *dither) {
+  return atm::run_blue_noise(picks, n, size, ftab, dither);
+}
+
+// the array `build.clj:45-51` writes to data/bluenoise.raw: dither / size / size as float32, density-function(sigma)
+extern "C" int sfsim_blue_noise_texture(const int *picks, int n, int size, double sigma, float *out) {
+  if (!out) return atm::fail("out is NULL");
+  if (size < 2 || size > 1024) return atm::fail("the dither array size must be in [2, 1024]");
+  if (!(sigma > 0)) return atm::fail("sigma must be positive");
+  const int offset = size / 2;
+  std::vector<double> ftab((size_t)size * size);
+  for (int dy = -offset; dy < size - offset; dy++)
+    for (int dx = -offset; dx < size - offset; dx++)     // density-function, bluenoise.clj:53-56
+      ftab[(size_t)(dy + offset) * size + (dx + offset)] = exp(-((double)(dx * dx + dy * dy) / (2.0 * sigma * sigma)));
+  std::vector<int> dither((size_t)size * size);
+  if (atm::run_blue_noise(picks, n, size, ftab.data(), dither.data())) return 1;
+  for (size_t i = 0; i < dither.size(); i++) out[i] = (float)(((double)dither[i] / (double)size) / (double)size);
+  return 0;
 }

@@ -75,3 +75,38 @@ def test_invalid_arguments():
         worley.worley_noise(3, 16, grid=np.zeros((3, 3, 3, 3)))        # size not a multiple of divisions
     with pytest.raises(TypeError):
         worley.worley_noise(2, 4, grid=np.zeros((2, 2, 3)))
+
+
+# ---------------------------------------------------------------- blue noise (bluenoise.clj)
+
+def test_blue_noise_matches_the_oracle_decision_for_decision():
+    """Every arg-max / arg-min of the void-and-cluster phases must fall on the same element as in the CPU oracle (which
+    reproduces t_bluenoise.clj:105-130): the dither arrays are equal as integers."""
+    from sfsim_b200 import bluenoise
+    for m, n, sigma, seed in ((16, 25, 1.5, 1), (2, 1, 1.5, 2), (9, 8, 1.9, 3), (64, 409, 1.5, 4)):   # 64: build.clj:47-50
+        rng = np.random.default_rng(seed)
+        picks = rng.permutation(m * m)[:n]
+        got = bluenoise.blue_noise(m, n, sigma, picks=picks)
+        want = orc.blue_noise(m, picks, sigma=sigma)
+        np.testing.assert_array_equal(got, want)
+        assert sorted(got.tolist()) == list(range(m * m))
+
+
+def test_blue_noise_reference_facts():
+    """t_bluenoise.clj:113-130 chained: seed [true false false true] of size 2 gives the dither array [0 3 2 1]"""
+    from sfsim_b200 import bluenoise
+    np.testing.assert_array_equal(bluenoise.blue_noise(2, 2, 1.5, picks=[0, 3]), [0, 3, 2, 1])
+    tex = bluenoise.blue_noise_texture(2, 2, 1.5, picks=[0, 3])
+    np.testing.assert_array_equal(tex, np.array([0, 3, 2, 1], dtype=np.float32) / 4)
+
+
+def test_blue_noise_texture_of_the_build_task():
+    from sfsim_b200 import bluenoise
+    rng = np.random.default_rng(11)
+    m = bluenoise.noise_size
+    picks = rng.permutation(m * m)[:m * m // 10]
+    tex = bluenoise.blue_noise_texture(picks=picks)
+    want = orc.blue_noise(m, picks, sigma=1.5).astype(np.float64) / m / m
+    np.testing.assert_array_equal(tex, want.astype(np.float32))
+    spectrum = np.abs(np.fft.fft2(tex.reshape(m, m) - tex.mean())) ** 2
+    assert spectrum[:4, :4].sum() - spectrum[0, 0] < 0.01 * spectrum.sum()      # low frequencies are suppressed

@@ -82,3 +82,67 @@ def test_perlin_corner_wraparound():
                 corner = np.array([0.5 - x, 0.5 - y, 0.5 - z])
                 want += 0.125 * float(g @ corner)          # ease-curve(1/2) = 1/2 on every axis
     assert got == pytest.approx(want, abs=1e-12)
+
+
+# ---------------------------------------------------------------- blue noise, t_bluenoise.clj:48-130
+
+def test_blue_noise_helpers():
+    f1 = orc.density_function(1.0)
+    assert f1(0, 0) == pytest.approx(1.0, abs=1e-6)
+    for dx, dy in ((1, 0), (0, 1), (-1, 0), (0, -1)):
+        assert f1(dx, dy) == pytest.approx(np.exp(-0.5))
+    assert orc.density_function(2.0)(2, 0) == pytest.approx(np.exp(-0.5))
+    assert orc.argmax_with_mask([5, 3, 2], [True] * 3) == 0
+    assert orc.argmax_with_mask([3, 5, 2], [True] * 3) == 1
+    assert orc.argmax_with_mask([3, 5, 2], [True, False, True]) == 0
+    assert orc.argmax_with_mask([3, 2, 5], [True, False, True]) == 2
+    assert orc.argmin_with_mask([2, 3, 5], [False] * 3) == 0
+    assert orc.argmin_with_mask([3, 2, 5], [False] * 3) == 1
+    assert orc.argmin_with_mask([3, 2, 5], [False, True, False]) == 0
+    assert orc.argmin_with_mask([3, 5, 2], [False, True, False]) == 2
+    assert [orc.wrap(x, m) for x, m in ((0, 5), (2, 5), (5, 5), (3, 5), (2, 4))] == [0, 2, 0, -2, -2]
+
+
+def test_blue_noise_density():
+    one, dx, dy = (lambda a, b: 1.0), (lambda a, b: float(a)), (lambda a, b: float(b))
+    assert orc.density_sample([False] * 4, 2, one, 0, 0) == 0.0
+    assert orc.density_sample([True, False, False, False], 2, one, 0, 0) == 1.0
+    assert orc.density_sample([True, False, False, False], 2, lambda a, b: 2.0, 0, 0) == 2.0
+    assert orc.density_sample([True] * 4, 2, one, 0, 0) == 4.0
+    assert orc.density_sample([True] * 9, 3, dx, 1, 1) == 0.0
+    assert orc.density_sample([True] * 9, 3, dy, 1, 1) == 0.0
+    assert orc.density_sample([False, False, True, False], 2, dx, 1, 1) == -1.0
+    assert orc.density_sample([False, True, False, False], 2, dy, 1, 1) == -1.0
+    assert orc.density_sample([True] * 9, 3, dx, 2, 2) == 0.0
+    assert orc.density_sample([True] * 9, 3, dy, 2, 2) == 0.0
+    np.testing.assert_array_equal(orc.density_array([True, False, False, False], 2, dx), [0.0, -1.0, 0.0, -1.0])
+    np.testing.assert_array_equal(orc.density_change([0.0, -1.0, 0.0, -1.0], 2, +1, dx, 0), [0.0, -2.0, 0.0, -2.0])
+    np.testing.assert_array_equal(orc.density_change([0.0, -1.0, 0.0, -1.0], 2, -1, dx, 0), [0.0, 0.0, 0.0, 0.0])
+
+
+def test_blue_noise_phases():
+    f19, f15 = orc.density_function(1.9), orc.density_function(1.5)
+    np.testing.assert_array_equal(orc.seed_pattern([True, False, False, False], 2, f19), [False, False, False, True])
+    np.testing.assert_array_equal(orc.seed_pattern([True, True, False, False], 2, f19), [True, False, False, True])
+    np.testing.assert_array_equal(orc.dither_phase1([True, False, False, False], 2, 1, f15), [0, 0, 0, 0])
+    np.testing.assert_array_equal(orc.dither_phase1([True, False, False, True], 2, 2, f15), [0, 0, 0, 1])
+    d, mask = orc.dither_phase2([True, False, False, True], 2, 2, [0, 0, 0, 1], f15)
+    np.testing.assert_array_equal(d, [0, 0, 0, 1])
+    np.testing.assert_array_equal(mask, [True, False, False, True])
+    d, mask = orc.dither_phase2([True, False, False, False], 2, 1, [0, 0, 0, 0], f15)
+    np.testing.assert_array_equal(d, [0, 0, 0, 1])
+    np.testing.assert_array_equal(mask, [True, False, False, True])
+    np.testing.assert_array_equal(orc.dither_phase3([True, False, False, True], 2, 2, [0, 0, 0, 1], f15), [0, 3, 2, 1])
+
+
+def test_blue_noise_is_a_permutation_with_blue_spectrum():
+    """blue-noise (bluenoise.clj:175-185): every rank 0 .. m^2 - 1 exactly once; thresholding at any level leaves no
+    two set pixels closer than the seed pattern allows (weak check: low frequencies are suppressed)."""
+    m, n = 16, 25
+    rng = np.random.default_rng(3)
+    picks = rng.permutation(m * m)[:n]
+    dither = orc.blue_noise(m, picks, sigma=1.5)
+    assert sorted(dither.tolist()) == list(range(m * m))
+    spectrum = np.abs(np.fft.fft2(dither.reshape(m, m) - dither.mean())) ** 2
+    low = spectrum[:3, :3].sum() - spectrum[0, 0]
+    assert low < 0.02 * spectrum.sum()
