@@ -208,6 +208,10 @@ struct Builder {
   bool use_graph = true;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // [1]: the same DAG with the per-stage event records
   bool capturing = false;
+  // page-locked host destinations of the four file tables (the one-shot call on one GPU): the downloads are then
+  // nodes of the build graph, and the 12.5 MB Mie-strength file, finished after the first iteration, leaves the
+  // device while the remaining iterations run
+  float *host_out[4] = {nullptr, nullptr, nullptr, nullptr};
   // pinned staging for downloads into pageable host memory
   unsigned char *staging[2] = {nullptr, nullptr};
   cudaEvent_t staging_done[2] = {nullptr, nullptr};
@@ -535,9 +539,11 @@ static int builder_enqueue(Builder &b) {
                                      deout[(it + 1) & 1], side));                     // :89,92
     else
       CUDA_TRY(cudaMemsetAsync(de_next, 0, (size_t)b.ne * sizeof(float4), side));
-    if (it == 0)
+    if (it == 0) {
       TRY(file_table(b.M1, b.file_M, b.file_M_root));                                 // :101,105
-    else
+      if (b.host_out[3])
+        CUDA_TRY(cudaMemcpyAsync(b.host_out[3], b.file_M, (size_t)b.n4 * 12, cudaMemcpyDeviceToHost, side));
+    } else
       TRY(accumulate_s(ds.tab_a));                                                    // :96-97
     TRY(event_at(b, ev++, side_done[it]));
     CUDA_TRY(cudaEventRecord(side_done[it], side));
@@ -592,6 +598,8 @@ static int builder_enqueue(Builder &b) {
     CUDA_TRY(cudaMemsetAsync(b.Eacc, 0, (size_t)b.ne * sizeof(float4), side));       // :76 E = 0
     e_cur = b.Eacc;
     TRY(file_table(b.M1, b.file_M, b.file_M_root));                                   // :101,105
+    if (b.host_out[3])
+      CUDA_TRY(cudaMemcpyAsync(b.host_out[3], b.file_M, (size_t)b.n4 * 12, cudaMemcpyDeviceToHost, side));
   } else {
     TRY(accumulate_s(ds.tab_a));                                                      // :96-97 (last order)
     if (sharded_side) {
@@ -602,6 +610,9 @@ static int builder_enqueue(Builder &b) {
   }
   LAUNCH(launch_resample_2d(P, 1, e_cur, nullptr, nullptr, b.file_E, side));          // :99,103
   TRY(file_table(s_cur, b.file_S, b.file_S_root));                                    // :100,104
+  if (b.host_out[2]) CUDA_TRY(cudaMemcpyAsync(b.host_out[2], b.file_S, (size_t)b.n4 * 12, cudaMemcpyDeviceToHost, side));
+  if (b.host_out[1]) CUDA_TRY(cudaMemcpyAsync(b.host_out[1], b.file_E, (size_t)b.ne * 12, cudaMemcpyDeviceToHost, side));
+  if (b.host_out[0]) CUDA_TRY(cudaMemcpyAsync(b.host_out[0], b.file_T, (size_t)b.nt * 12, cudaMemcpyDeviceToHost, side));
   TRY(order_after(b, ev, side, st));
   if (sharded_side) TRY(peer_barrier(b, 0, st));                                      // rank 0 holds every pair's texels
   TRY(stage_end(b));
@@ -909,14 +920,18 @@ extern "C" int atmlut_builder_sync(void *builder) {
 // library-owned pinned buffers: the copy engine fills one while the host thread empties the other.
 static const size_t kStagingBytes = 4u << 20;
 
-static int copy_out(Builder *b, void *dst, const void *src, size_t bytes) {
+// neither allocated by cudaMallocHost / atmlut_host_alloc nor registered with cudaHostRegister
+static bool is_pageable(const void *p) {
   cudaPointerAttributes attr;
-  cudaError_t e = cudaPointerGetAttributes(&attr, dst);
-  if (e != cudaSuccess) {
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
     cudaGetLastError();
-    attr.type = cudaMemoryTypeUnregistered;
+    return true;
   }
-  if (attr.type != cudaMemoryTypeUnregistered || bytes <= (256u << 10)) {
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static int copy_out(Builder *b, void *dst, const void *src, size_t bytes) {
+  if (!is_pageable(dst) || bytes <= (256u << 10)) {
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->main));
     return 0;
   }
@@ -1099,8 +1114,37 @@ extern "C" int atmlut_generate(const atmlut_planet *planet, const atmlut_scatter
     g_cache.cfg = *cfg;
     g_cache.device = g_device;
   }
-  int rc = atmlut_builder_run(g_cache.builder);
-  if (!rc) rc = atmlut_builder_download(g_cache.builder, transmittance, surface_radiance, ray_scatter, mie_strength);
+  // Page-locked destinations: the downloads become nodes of the build graph (re-captured when the pointers change).
+  Builder *b = (Builder *)g_cache.builder;
+  float *dst[4] = {transmittance, surface_radiance, ray_scatter, mie_strength};
+  bool in_graph = true;
+  for (float *p : dst) in_graph = in_graph && p && !is_pageable(p);
+  int rc = 0;
+  if (in_graph) {
+    if (memcmp(b->host_out, dst, sizeof dst) != 0) {
+      CUDA_TRY(cudaStreamSynchronize(b->main));
+      for (auto &g : b->graph_exec)
+        if (g) {
+          cudaGraphExecDestroy(g);
+          g = nullptr;
+        }
+      memcpy(b->host_out, dst, sizeof dst);
+    }
+    rc = atmlut_builder_run(g_cache.builder);
+    if (!rc) rc = atmlut_builder_sync(g_cache.builder);
+  } else {
+    if (b->host_out[0]) {
+      CUDA_TRY(cudaStreamSynchronize(b->main));
+      for (auto &g : b->graph_exec)
+        if (g) {
+          cudaGraphExecDestroy(g);
+          g = nullptr;
+        }
+      memset(b->host_out, 0, sizeof b->host_out);
+    }
+    rc = atmlut_builder_run(g_cache.builder);
+    if (!rc) rc = atmlut_builder_download(g_cache.builder, transmittance, surface_radiance, ray_scatter, mie_strength);
+  }
   if (rc) drop_generate_cache();
   return rc;
 }
