@@ -7,8 +7,8 @@ ARCH = -gencode arch=compute_100a,code=sm_100a
 # arithmetic; the hot loops ask for their FMAs explicitly (fmaf / fma).
 NVCCFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
 CSRC = sfsim_b200/csrc
-SRCS = $(CSRC)/atm_api.cu $(CSRC)/atm_tables.cu $(CSRC)/atm_lookup.cu $(CSRC)/atm_batch.cu $(CSRC)/noise.cu
-HDRS = $(CSRC)/atm_math.cuh $(CSRC)/atm_device.cuh $(CSRC)/atm_kernel_common.cuh $(CSRC)/atm_tables.h $(CSRC)/atm_api_internal.h include/sfsim_atmosphere.h include/sfsim_noise.h
+SRCS = $(CSRC)/atm_api.cu $(CSRC)/atm_tables.cu $(CSRC)/atm_lookup.cu $(CSRC)/atm_batch.cu $(CSRC)/noise.cu $(CSRC)/cubemap.cu
+HDRS = $(CSRC)/atm_math.cuh $(CSRC)/atm_device.cuh $(CSRC)/atm_kernel_common.cuh $(CSRC)/atm_tables.h $(CSRC)/atm_api_internal.h include/sfsim_atmosphere.h include/sfsim_noise.h include/sfsim_cubemap.h
 OBJS = $(SRCS:.cu=.o)
 
 all: libsfsim_atmosphere.so

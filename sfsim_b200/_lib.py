@@ -54,7 +54,7 @@ OPT_GRAPH, OPT_BARRIER_TIMEOUT_MS = 1, 2
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
-# every symbol include/sfsim_atmosphere.h and include/sfsim_noise.h declare
+# every symbol include/sfsim_atmosphere.h, include/sfsim_noise.h and include/sfsim_cubemap.h declare
 EXPORTS = [
     "atmlut_init", "atmlut_destroy", "atmlut_stream", "atmlut_last_error", "atmlut_device_count", "atmlut_default_config",
     "atmlut_generate", "atmlut_generate_multi",
@@ -76,6 +76,11 @@ EXPORTS = [
     # include/sfsim_noise.h
     "sfsim_worley_noise", "sfsim_perlin_noise", "sfsim_worley_distances", "sfsim_perlin_samples",
     "sfsim_blue_noise", "sfsim_blue_noise_texture",
+    # include/sfsim_cubemap.h
+    "sfsim_cubemap_default_config", "sfsim_cubemap_world_create", "sfsim_cubemap_world_destroy",
+    "sfsim_cubemap_world_set_elevation", "sfsim_cubemap_world_set_color", "sfsim_cubemap_world_set_elevation_tile",
+    "sfsim_cubemap_world_set_color_tile", "sfsim_cubemap_tiles", "sfsim_cubemap_tiles_timed", "sfsim_cubemap_tile_shard",
+    "sfsim_cubemap_project_onto_globe_batch", "sfsim_cubemap_normal_for_point_batch", "sfsim_cubemap_geodetic_batch",
 ]
 
 _lib = None
@@ -112,6 +117,9 @@ def load():
         lib.atmlut_builder_stage_ms.argtypes = [C.c_void_p, C.c_int, c_float_p]
         lib.atmlut_builder_work.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
         lib.atmlut_builder_counter.argtypes = [C.c_void_p, C.c_int, c_double_p]
+        lib.sfsim_cubemap_default_config.restype = None
+        lib.sfsim_cubemap_world_destroy.restype = None
+        lib.sfsim_cubemap_world_destroy.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
