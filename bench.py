@@ -223,6 +223,13 @@ class Runner:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def max_over_ranks(self, value):
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
     def time_steps(self, builder, steps, warmup):
         """(ms per step, max over ranks): CUDA events on the builder's stream around every build, a 512 MiB
         write between steps so that no table survives in L2."""
@@ -248,6 +255,69 @@ class Runner:
         if self.world > 1:
             self.dist.all_reduce(total, op=self.dist.ReduceOp.MAX)
         return float(total.item()) / steps, wall
+
+
+def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
+    """SURVEY.md section 8(f) row 4, `clj -T:build cube-maps` (build.clj:294-310): every tile of one output level of the
+    cube-map pyramid with the shipped constants (675-pixel map tiles, 65 / 129-pixel cube tiles) from synthetic rasters
+    resident in device memory.  Tiles are independent: rank r takes every world-th tile, no exchange (weak scaling is
+    the natural mode; here the level is a fixed job, so this is strong scaling of the 1536-tile level)."""
+    import numpy as np
+    from oracle import cubemap as ocm                 # synthetic rasters and the CPU baseline only
+    from sfsim_b200 import cubemap
+    in_level = out_level - 3                           # build.clj:300-310
+    cfg = cubemap.make_config(in_level, out_level)
+    ls, lc, lw = max(0, min(4, in_level)), max(0, min(5, in_level + 1)), max(0, min(4, in_level + 1))
+    elev, day, night = ocm.synthetic_world(675, sorted({ls, lw}), [lc], seed=1)
+    w = cubemap.World(675)
+    for level, a in elev.items():
+        w.set_elevation(level, a)
+    w.set_color(False, lc, day[lc])
+    w.set_color(True, lc, night[lc])
+    tiles = cubemap.tile_shard(out_level, rank, world)
+    total_tiles = 6 * 4 ** out_level
+    pixels = total_tiles * cfg.color_tilesize ** 2
+    for _ in range(3):
+        w.time_cube_map_tiles(cfg, tiles)
+    ms = []
+    for _ in range(5):
+        runner.barrier()
+        ms.append(runner.max_over_ranks(w.time_cube_map_tiles(cfg, tiles)))
+    dev_ms = float(np.median(ms))
+    # end to end: the streamed level call -- tile list in, every tile's five arrays delivered to a host callback in
+    # page-locked memory (691 MB per 1536 tiles cross PCIe), copies overlapped with the kernels of the next batch
+    per_tile = 2 * cfg.color_tilesize ** 2 * 4 + cfg.color_tilesize * ((cfg.color_tilesize + 3) & ~3) + \
+        cfg.surface_tilesize ** 2 * 12 + cfg.color_tilesize ** 2 * 15
+    d2h = per_tile * len(tiles)
+    w.time_cube_map_level(cfg, rank, world)
+    runner.barrier()
+    t0 = time.perf_counter()
+    delivered = 0
+    for _ in range(3):
+        delivered = w.time_cube_map_level(cfg, rank, world)[1]
+    runner.barrier()
+    e2e_s = (time.perf_counter() - t0) / 3
+    assert delivered == len(tiles)
+    res = {"workload": "cube-map tiles, output level %d (6 x %d x %d tiles, in-level %d), map tiles 675 px, cube tiles 65 / 129 "
+                       "px, synthetic rasters (elevation levels %s, colour level %d)" % (
+                           out_level, 1 << out_level, 1 << out_level, in_level, sorted({ls, lw}), lc),
+           "tiles": total_tiles, "ms_per_level": dev_ms, "colour_pixels_per_s": pixels / (dev_ms * 1e-3),
+           "tiles_per_s": total_tiles / (dev_ms * 1e-3),
+           "e2e": {"tiles_per_s": total_tiles / e2e_s, "seconds_per_level": e2e_s, "d2h_bytes_per_level_this_rank": d2h,
+                   "h2d_bytes_per_level_this_rank": int(tiles.nbytes), "api": "sfsim_cubemap_level (batches of 256 tiles, counting "
+                   "callback)", "host_buffers": "library-owned page-locked staging, two sets"},
+           "bound": "FP64 pipe / issue slots (ncu: profiles/r2/); DRAM traffic 1.2 GB per level = the outputs"}
+    if with_cpu and rank == 0:
+        ow = ocm.OracleWorld(675, elev, day, night)
+        sample = [tuple(t) for t in tiles[:: max(1, len(tiles) // 4)][:4]]
+        t0 = time.perf_counter()
+        for face, b, a in sample:
+            ow.make_cube_map_tile(face, in_level, out_level, b, a)
+        cpu_s = (time.perf_counter() - t0) / len(sample)
+        res["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "tiles/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d tiles of the same level with the C restatement (OpenMP over pixel rows)" % len(sample)}
+    w.close()
+    return res
 
 
 def run_b200(args):
@@ -406,6 +476,8 @@ def run_b200(args):
                 if identical is not None:
                     identical["stress_" + args.mode] = extras["stress"]["sharded_identical"]
             sb.close()
+        if args.workload == "shipped":
+            extras["cubemap"] = cubemap_bench(rank, world, runner, with_cpu=not args.no_cpu_baseline and world == 1)
 
     # ---------------- rooflines
     peaks = {}
@@ -453,9 +525,7 @@ def run_b200(args):
                                 "note": "two float4 output tables per launch; the kernel is SFU-bound, not HBM-bound"},
                         "peak_source": "measured on this pool's B200 by tools/pipe_peaks.cu (profiles/pipe_peaks_b200.json)",
                         "algorithmic_units": "2 exponentials per overall-extinction sample (one per scatter component); "
-                                             "samples counted on the device.  One exponential in four is evaluated on "
-                                             "the FMA pipe (ex2_poly2), so the fraction can exceed what the MUFU pipe "
-                                             "alone would allow",
+                                             "samples counted on the device, every one of them on the MUFU pipe",
                         "esamples_per_launch": work["esamples_first_order"], "launch_ms": first_ms}
         # ray-scatter from the dJ table: bound by shared-memory wavefronts.  Floor per 4-D lookup of one warp:
         # 4 x LDS.128 (16 wavefronts) for the bilinear corners + 1 x STS.128 (4) for its share of the blended tile.

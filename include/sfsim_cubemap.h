@@ -69,6 +69,23 @@ int sfsim_cubemap_tiles_timed(void *world, const sfsim_cubemap_config *cfg, int 
  * globe.clj:41 (face, b, a); writes up to `capacity` triples and returns the count through *ntiles */
 int sfsim_cubemap_tile_shard(int out_level, int rank, int world_size, int capacity, int *tiles, int *ntiles);
 
+/* ---- make-cube-map for a whole level, streamed (the call `clj -T:build cube-map` would make) ----
+ * Generates the tiles rank `rank` of `world_size` owns, `batch_tiles` at a time, and hands every finished tile to `fn`
+ * in the order of sfsim_cubemap_tile_shard.  The pointers address page-locked host memory owned by the library and are
+ * valid during the call only: the callback encodes / writes the five files of the tile (globe.clj:74-78).  While the
+ * callback works on one batch, the next is in flight over PCIe and the one after is being computed.  A non-zero
+ * return value of `fn` aborts the level. */
+typedef int (*sfsim_cubemap_tile_fn)(void *user, int face, int b, int a, const unsigned char *day,
+                                     const unsigned char *night, const unsigned char *water, const float *surface,
+                                     const float *normals, const signed char *normal_bytes);
+int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg, int rank, int world_size, int batch_tiles,
+                        sfsim_cubemap_tile_fn fn, void *user);
+/* a ready-made callback that reads the first and last byte of every array and counts the tiles (user = long long[2]:
+ * tiles, byte sum): measures the pipeline without a consumer */
+int sfsim_cubemap_tile_counter(void *user, int face, int b, int a, const unsigned char *day, const unsigned char *night,
+                               const unsigned char *water, const float *surface, const float *normals,
+                               const signed char *normal_bytes);
+
 /* ---- the point-wise functions of sfsim.cubemap at arbitrary arguments (known-answer and parity tests) ---- */
 /* project-onto-globe (cubemap.clj:336-342): p double[n][3] -> out double[n][3] */
 int sfsim_cubemap_project_onto_globe_batch(void *world, int in_level, double radius, int n, const double *p, double *out);

@@ -80,6 +80,7 @@ EXPORTS = [
     "sfsim_cubemap_default_config", "sfsim_cubemap_world_create", "sfsim_cubemap_world_destroy",
     "sfsim_cubemap_world_set_elevation", "sfsim_cubemap_world_set_color", "sfsim_cubemap_world_set_elevation_tile",
     "sfsim_cubemap_world_set_color_tile", "sfsim_cubemap_tiles", "sfsim_cubemap_tiles_timed", "sfsim_cubemap_tile_shard",
+    "sfsim_cubemap_level", "sfsim_cubemap_tile_counter",
     "sfsim_cubemap_project_onto_globe_batch", "sfsim_cubemap_normal_for_point_batch", "sfsim_cubemap_geodetic_batch",
 ]
 

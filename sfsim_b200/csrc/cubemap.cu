@@ -319,11 +319,18 @@ struct World {
   short *elevation[kLevels] = {};
   unsigned char *day[kLevels] = {};
   unsigned char *night[kLevels] = {};
-  // outputs of the last batch (grown on demand) and the tile list
-  void *out[6] = {};
-  size_t out_bytes[6] = {};
-  int *tiles = nullptr;
-  int tiles_capacity = 0;
+  // two sets of device outputs (grown on demand) with their tile lists: the one-batch calls use set 0, the level
+  // pipeline alternates; page-locked host images of both sets and a copy stream for the pipeline
+  struct OutSet {
+    void *dev[6] = {};
+    size_t bytes[6] = {};
+    int *tiles = nullptr;
+    int tiles_capacity = 0;
+    void *host[6] = {};
+    size_t host_bytes[6] = {};
+    cudaEvent_t computed = nullptr, copied = nullptr;
+  } sets[2];
+  cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
@@ -383,9 +390,10 @@ static int make_job(const World &w, const sfsim_cubemap_config *cfg, TileJob &jo
 }
 
 static int run_tiles(World *w, const sfsim_cubemap_config *cfg, int ntiles, const int *tiles, const bool want[6],
-                     float *ms) {
+                     float *ms, int set_index = 0) {
   if (ensure_init()) return 1;
   if (!w) return fail("world must not be NULL");
+  World::OutSet &set = w->sets[set_index];
   TileJob job;
   if (make_job(*w, cfg, job)) return 1;
   if (ntiles < 0 || (ntiles > 0 && !tiles)) return fail("tiles must not be NULL");
@@ -410,38 +418,38 @@ static int run_tiles(World *w, const sfsim_cubemap_config *cfg, int ntiles, cons
   const size_t need[6] = {cpix * 4 * ntiles, cpix * 4 * ntiles, (size_t)job.ct * job.wpitch * ntiles,
                           spix * 12 * ntiles, cpix * 12 * ntiles, cpix * 3 * ntiles};
   for (int k = 0; k < 6; k++)
-    if (want[k] && w->out_bytes[k] < need[k]) {
-      CUDA_TRY(cudaStreamSynchronize(stream()));
-      cudaFree(w->out[k]);
-      w->out[k] = nullptr;
-      w->out_bytes[k] = 0;
-      CUDA_TRY(cudaMalloc(&w->out[k], need[k]));
-      w->out_bytes[k] = need[k];
+    if (want[k] && set.bytes[k] < need[k]) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      cudaFree(set.dev[k]);
+      set.dev[k] = nullptr;
+      set.bytes[k] = 0;
+      CUDA_TRY(cudaMalloc(&set.dev[k], need[k]));
+      set.bytes[k] = need[k];
     }
-  if (w->tiles_capacity < ntiles) {
-    CUDA_TRY(cudaStreamSynchronize(stream()));
-    cudaFree(w->tiles);
-    w->tiles = nullptr;
-    w->tiles_capacity = 0;
-    CUDA_TRY(cudaMalloc((void **)&w->tiles, (size_t)ntiles * 3 * sizeof(int)));
-    w->tiles_capacity = ntiles;
+  if (set.tiles_capacity < ntiles) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(set.tiles);
+    set.tiles = nullptr;
+    set.tiles_capacity = 0;
+    CUDA_TRY(cudaMalloc((void **)&set.tiles, (size_t)ntiles * 3 * sizeof(int)));
+    set.tiles_capacity = ntiles;
   }
   cudaStream_t st = stream();
-  CUDA_TRY(cudaMemcpyAsync(w->tiles, tiles, (size_t)ntiles * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(set.tiles, tiles, (size_t)ntiles * 3 * sizeof(int), cudaMemcpyHostToDevice, st));
   TileOut out;
-  out.day = want[0] ? (uchar4 *)w->out[0] : nullptr;
-  out.night = want[1] ? (uchar4 *)w->out[1] : nullptr;
-  out.water = want[2] ? (unsigned char *)w->out[2] : nullptr;
-  out.surface = want[3] ? (float *)w->out[3] : nullptr;
-  out.normals = want[4] ? (float *)w->out[4] : nullptr;
-  out.normal_bytes = want[5] ? (signed char *)w->out[5] : nullptr;
+  out.day = want[0] ? (uchar4 *)set.dev[0] : nullptr;
+  out.night = want[1] ? (uchar4 *)set.dev[1] : nullptr;
+  out.water = want[2] ? (unsigned char *)set.dev[2] : nullptr;
+  out.surface = want[3] ? (float *)set.dev[3] : nullptr;
+  out.normals = want[4] ? (float *)set.dev[4] : nullptr;
+  out.normal_bytes = want[5] ? (signed char *)set.dev[5] : nullptr;
   const WorldDev dev = device_view(*w);
   if (ms) CUDA_TRY(cudaEventRecord(w->ev[0], st));
   if (out.water) CUDA_TRY(cudaMemsetAsync(out.water, 0, need[2], st));   // the pad columns of make-byte-image
   if (out.surface)
-    k_cube_surface<<<dim3((unsigned)((spix + 127) / 128), ntiles), 128, 0, st>>>(dev, job, w->tiles, out);
+    k_cube_surface<<<dim3((unsigned)((spix + 127) / 128), ntiles), 128, 0, st>>>(dev, job, set.tiles, out);
   if (out.day || out.night || out.water || out.normals || out.normal_bytes)
-    k_cube_color<<<dim3((unsigned)((cpix + 127) / 128), ntiles), 128, 0, st>>>(dev, job, w->tiles, out);
+    k_cube_color<<<dim3((unsigned)((cpix + 127) / 128), ntiles), 128, 0, st>>>(dev, job, set.tiles, out);
   CUDA_TRY(cudaGetLastError());
   if (ms) {
     CUDA_TRY(cudaEventRecord(w->ev[1], st));
@@ -486,6 +494,8 @@ static int run_points(World *w, int n, const double *in_a, size_t in_a_count, co
 using namespace atm;
 using namespace atm::cube;
 
+extern "C" int sfsim_cubemap_tile_shard(int out_level, int rank, int world_size, int capacity, int *tiles, int *ntiles);
+
 extern "C" void sfsim_cubemap_default_config(sfsim_cubemap_config *cfg) {
   if (!cfg) return;
   cfg->in_level = -3;   // build.clj:300-302: (cube-map {:in-level -3 :out-level 0})
@@ -523,8 +533,15 @@ extern "C" void sfsim_cubemap_world_destroy(void *world) {
     cudaFree(w->day[l]);
     cudaFree(w->night[l]);
   }
-  for (auto &o : w->out) cudaFree(o);
-  cudaFree(w->tiles);
+  cudaDeviceSynchronize();
+  for (auto &set : w->sets) {
+    for (auto &o : set.dev) cudaFree(o);
+    for (auto &h : set.host) cudaFreeHost(h);
+    cudaFree(set.tiles);
+    if (set.computed) cudaEventDestroy(set.computed);
+    if (set.copied) cudaEventDestroy(set.copied);
+  }
+  if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
   for (auto &e : w->ev)
     if (e) cudaEventDestroy(e);
   delete w;
@@ -599,7 +616,7 @@ extern "C" int sfsim_cubemap_tiles(void *world, const sfsim_cubemap_config *cfg,
   const size_t bytes[6] = {cpix * 4 * ntiles, cpix * 4 * ntiles, (size_t)job.ct * job.wpitch * ntiles,
                            spix * 12 * ntiles, cpix * 12 * ntiles, cpix * 3 * ntiles};
   for (int k = 0; k < 6; k++)
-    if (want[k]) CUDA_TRY(cudaMemcpyAsync(dst[k], w->out[k], bytes[k], cudaMemcpyDeviceToHost, stream()));
+    if (want[k]) CUDA_TRY(cudaMemcpyAsync(dst[k], w->sets[0].dev[k], bytes[k], cudaMemcpyDeviceToHost, stream()));
   CUDA_TRY(cudaStreamSynchronize(stream()));
   return 0;
 }
@@ -609,6 +626,82 @@ extern "C" int sfsim_cubemap_tiles_timed(void *world, const sfsim_cubemap_config
   if (!ms) return fail("ms must not be NULL");
   const bool want[6] = {true, true, true, true, true, true};
   return run_tiles((World *)world, cfg, ntiles, tiles, want, ms);
+}
+
+// make-cube-map for this rank's share of a level (globe.clj:41-72), streamed: while the host callback consumes batch
+// i - 1 from page-locked memory, the copy engine brings batch i back and the SMs compute batch i + 1.
+extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg, int rank, int world_size, int batch_tiles,
+                                   sfsim_cubemap_tile_fn fn, void *user) {
+  World *w = (World *)world;
+  if (ensure_init()) return 1;
+  if (!w) return fail("world must not be NULL");
+  if (!fn) return fail("the tile callback must not be NULL");
+  TileJob job;
+  if (make_job(*w, cfg, job)) return 1;
+  if (batch_tiles < 1 || batch_tiles > 65535) return fail("batch_tiles must be in [1, 65535]");
+  int count = 0;
+  if (sfsim_cubemap_tile_shard(cfg->out_level, rank, world_size, 0, nullptr, &count)) return 1;
+  std::vector<int> tiles((size_t)std::max(count, 1) * 3);
+  if (sfsim_cubemap_tile_shard(cfg->out_level, rank, world_size, count, tiles.data(), &count)) return 1;
+  if (count == 0) return 0;
+  batch_tiles = std::min(batch_tiles, count);
+  const size_t cpix = (size_t)job.ct * job.ct, spix = (size_t)job.st * job.st;
+  const size_t per_tile[6] = {cpix * 4, cpix * 4, (size_t)job.ct * job.wpitch, spix * 12, cpix * 12, cpix * 3};
+  if (!w->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+  for (auto &set : w->sets) {
+    if (!set.computed) CUDA_TRY(cudaEventCreateWithFlags(&set.computed, cudaEventDisableTiming));
+    if (!set.copied) CUDA_TRY(cudaEventCreateWithFlags(&set.copied, cudaEventDisableTiming));
+    for (int k = 0; k < 6; k++)
+      if (set.host_bytes[k] < per_tile[k] * batch_tiles) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFreeHost(set.host[k]);
+        set.host[k] = nullptr;
+        set.host_bytes[k] = 0;
+        CUDA_TRY(cudaMallocHost(&set.host[k], per_tile[k] * batch_tiles));
+        set.host_bytes[k] = per_tile[k] * batch_tiles;
+      }
+  }
+  const bool want[6] = {true, true, true, true, true, true};
+  const int nbatches = (count + batch_tiles - 1) / batch_tiles;
+  auto batch_size = [&](int i) { return std::min(batch_tiles, count - i * batch_tiles); };
+  auto deliver = [&](int i) -> int {       // hand the tiles of batch i to the host, in order
+    World::OutSet &set = w->sets[i & 1];
+    CUDA_TRY(cudaEventSynchronize(set.copied));
+    for (int t = 0; t < batch_size(i); t++) {
+      const int *tile = &tiles[(size_t)(i * batch_tiles + t) * 3];
+      if (fn(user, tile[0], tile[1], tile[2], (const unsigned char *)set.host[0] + per_tile[0] * t,
+             (const unsigned char *)set.host[1] + per_tile[1] * t, (const unsigned char *)set.host[2] + per_tile[2] * t,
+             (const float *)((const char *)set.host[3] + per_tile[3] * t),
+             (const float *)((const char *)set.host[4] + per_tile[4] * t),
+             (const signed char *)set.host[5] + per_tile[5] * t))
+        return fail("the tile callback reported an error");
+    }
+    return 0;
+  };
+  for (int i = 0; i < nbatches; i++) {
+    World::OutSet &set = w->sets[i & 1];
+    // the kernels of batch i overwrite the device set batch i - 2 used: its copy must have left the device
+    if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(stream(), set.copied, 0));
+    if (run_tiles(w, cfg, batch_size(i), &tiles[(size_t)i * batch_tiles * 3], want, nullptr, i & 1)) return 1;
+    CUDA_TRY(cudaEventRecord(set.computed, stream()));
+    CUDA_TRY(cudaStreamWaitEvent(w->copy_stream, set.computed, 0));
+    // the host image of this set was consumed by deliver(i - 2), which ran before this point
+    for (int k = 0; k < 6; k++)
+      CUDA_TRY(cudaMemcpyAsync(set.host[k], set.dev[k], per_tile[k] * batch_size(i), cudaMemcpyDeviceToHost, w->copy_stream));
+    CUDA_TRY(cudaEventRecord(set.copied, w->copy_stream));
+    if (i >= 1 && deliver(i - 1)) return 1;
+  }
+  return deliver(nbatches - 1);
+}
+
+extern "C" int sfsim_cubemap_tile_counter(void *user, int, int, int, const unsigned char *day, const unsigned char *night,
+                                          const unsigned char *water, const float *surface, const float *normals,
+                                          const signed char *normal_bytes) {
+  long long *acc = (long long *)user;
+  if (!acc) return 1;
+  acc[0] += 1;
+  acc[1] += day[0] + night[0] + water[0] + (surface[0] != 0.f) + (normals[0] != 0.f) + normal_bytes[0];
+  return 0;
 }
 
 extern "C" int sfsim_cubemap_tile_shard(int out_level, int rank, int world_size, int capacity, int *tiles, int *ntiles) {

@@ -28,6 +28,10 @@ class CubemapConfig(C.Structure):
         return (1 << self.sublevel) * (self.surface_tilesize - 1) + 1
 
 
+TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_void_p)
+
+
 def make_config(in_level, out_level, **kw):
     """The constants of make-cube-map (globe.clj:32-40) overridden by keyword."""
     cfg = CubemapConfig()
@@ -297,13 +301,44 @@ class World:
         check(_lib.load().sfsim_cubemap_tiles_timed(self._h, C.byref(cfg), len(tiles), _lib.ptr(tiles), C.byref(ms)))
         return ms.value
 
-    def make_cube_map(self, in_level, out_level, rank=0, world_size=1, batch=256, **kw):
-        """make-cube-map (globe.clj:29-80): yields ((face, b, a), tile dict) for this rank's tiles of the output level;
-        the caller encodes and writes them (spit-jpg, spit-bytes-gz, spit-floats-gz, spit-normals)."""
+    def time_cube_map_level(self, cfg, rank=0, world_size=1, batch=256):
+        """seconds for sfsim_cubemap_level with the library's counting callback (no consumer): (seconds, tiles)"""
+        import time
+        acc = (C.c_longlong * 2)(0, 0)
+        lib = _lib.load()
+        fn = C.cast(lib.sfsim_cubemap_tile_counter, TILE_FN)
+        t0 = time.perf_counter()
+        check(lib.sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch), fn, C.byref(acc)))
+        return time.perf_counter() - t0, int(acc[0])
+
+    def make_cube_map(self, in_level, out_level, on_tile, rank=0, world_size=1, batch=256, **kw):
+        """make-cube-map (globe.clj:29-80) for this rank's tiles of the output level, streamed: `on_tile((face, b, a),
+        tile)` is called for every tile with a dict of array views (day, night, water, surface, normals, normal_bytes)
+        into page-locked memory that is valid during the call only -- the place to encode and write the tile's five files
+        (spit-jpg, spit-bytes-gz, spit-floats-gz, spit-normals).  While the callback works on one batch the next one
+        crosses PCIe and the one after is being computed.  Returns the number of tiles delivered."""
         cfg = make_config(in_level, out_level, width=self.width, **kw)
-        todo = tile_shard(out_level, rank, world_size)
-        for s in range(0, len(todo), batch):
-            part = todo[s:s + batch]
-            out = self.make_cube_map_tiles(cfg, part)
-            for t, (face, b, a) in enumerate(part):
-                yield (int(face), int(b), int(a)), {k: v[t] for k, v in out.items()}
+        st, ct = cfg.surface_tilesize, cfg.color_tilesize
+        pitch = (ct + 3) & ~3
+        shapes = (("day", C.c_ubyte, (ct, ct, 4)), ("night", C.c_ubyte, (ct, ct, 4)), ("water", C.c_ubyte, (ct, pitch)),
+                  ("surface", C.c_float, (st, st, 3)), ("normals", C.c_float, (ct, ct, 3)), ("normal_bytes", C.c_byte, (ct, ct, 3)))
+        delivered = [0]
+        failure = []
+
+        def trampoline(_user, face, b, a, *ptrs):
+            try:
+                tile = {name: np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
+                        for (name, ctype, shape), p in zip(shapes, ptrs)}
+                on_tile((face, b, a), tile)
+                delivered[0] += 1
+                return 0
+            except BaseException as e:      # an exception must not unwind through the C frames
+                failure.append(e)
+                return 1
+
+        fn = TILE_FN(trampoline)
+        status = _lib.load().sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch), fn, None)
+        if failure:
+            raise failure[0]
+        check(status)
+        return delivered[0]

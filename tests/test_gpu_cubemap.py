@@ -206,3 +206,39 @@ def test_a_whole_level_has_the_properties_of_the_pyramid():
     assert (out["water"][:, :, 129:] == 0).all()
     assert np.isfinite(out["surface"]).all() and np.abs(out["surface"]).max() < R
     gw.close()
+
+
+def test_the_streamed_level_delivers_every_tile_once_and_equals_the_batch_call():
+    width = 32
+    elev, day, night = ocm.synthetic_world(width, [0, 1], [1], seed=17)
+    gw = cubemap.World(width)
+    for level in (0, 1):
+        gw.set_elevation(level, elev[level])
+    gw.set_color(False, 1, day[1])
+    gw.set_color(True, 1, night[1])
+    cfg = cubemap.make_config(0, 2, width=width, surface_tilesize=17)
+    for rank, world_size, batch in ((0, 1, 7), (1, 3, 5), (0, 1, 200)):      # ragged last batch, one batch, a shard
+        tiles = cubemap.tile_shard(2, rank, world_size)
+        want = gw.make_cube_map_tiles(cfg, tiles)
+        seen = []
+
+        def on_tile(key, tile):
+            n = len(seen)
+            assert key == tuple(tiles[n])
+            for k, v in tile.items():
+                assert v.tobytes() == want[k][n].tobytes(), (key, k)
+            seen.append(key)
+
+        assert gw.make_cube_map(0, 2, on_tile, rank=rank, world_size=world_size, batch=batch, surface_tilesize=17) == len(tiles)
+        assert len(seen) == len(tiles)
+
+    class Stop(Exception):
+        pass
+
+    def failing(key, tile):
+        raise Stop()
+
+    with pytest.raises(Stop):
+        gw.make_cube_map(0, 2, failing, batch=4, surface_tilesize=17)
+    assert gw.make_cube_map(0, 0, lambda key, tile: None, rank=7, world_size=8, surface_tilesize=17) == 0
+    gw.close()
