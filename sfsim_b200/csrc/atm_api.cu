@@ -197,6 +197,7 @@ struct Builder {
   float4 *tiles_a = nullptr, *tiles_b = nullptr;   // blended S tiles per (height, sphere direction)
   HalfDirInfo *half_info = nullptr;
   void *ray_samples = nullptr;             // per (pair, outer sample) records of the ray-scatter kernel
+  void *view_packs = nullptr;              // the view ray of every pair (launch_view_prepare)
   unsigned long long *counter = nullptr;
   const double *exp_tab = nullptr;
   std::vector<Stage> stages;
@@ -223,7 +224,7 @@ struct Builder {
       if (g) cudaGraphExecDestroy(g);
     void *ptrs[] = {T, dE, dE_new, Eacc, Eacc_new, R1, M1, dS, dS2, dJ, S, S_new, file_T, file_E, file_S, file_M,
                     sphere_dirs, sphere_w, half_dirs, half_w, dir_info, half_info, counter,
-                    tiles_a, tiles_b, flags, epochs, error_flag, ray_samples};
+                    tiles_a, tiles_b, flags, epochs, error_flag, ray_samples, view_packs};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     for (auto &s : stages) {
@@ -471,6 +472,14 @@ static int builder_enqueue(Builder &b) {
   CUDA_TRY(cudaMemsetAsync(b.error_flag, 0, sizeof(int), st));
   // peer-to-peer mode: nobody may store into a peer's tables before that peer has finished its previous run
   if (sharded_side) TRY(peer_barrier(b, 0, st));
+  // the view rays of this rank's pairs, once: the first-order kernel and the ray-scatter records both start from them
+  static const bool use_view_packs = !(getenv("ATMLUT_VIEW_PACK") && atoi(getenv("ATMLUT_VIEW_PACK")) == 0);   // A/B knob
+  const void *packs = nullptr;
+  if (use_view_packs) {
+    if (!b.view_packs) CUDA_TRY(cudaMalloc(&b.view_packs, view_pack_total_bytes(P)));
+    LAUNCH(launch_view_prepare(P, shard, b.he_count, b.view_packs, b.counter, st));
+    packs = b.view_packs;
+  }
   TRY(order_after(b, ev, st, side));   // the side stream starts after whatever the main stream did before
 
   // ---- side: 2-D tables and per-direction constants
@@ -485,7 +494,7 @@ static int builder_enqueue(Builder &b) {
   cudaEvent_t e_rays = nullptr;
   if (N > 0 && ray_scatter_uses_samples(P)) {
     if (!b.ray_samples) CUDA_TRY(cudaMalloc(&b.ray_samples, ray_sample_bytes(P, b.he_count)));
-    LAUNCH(launch_ray_prepare(P, shard, b.he_count, b.ray_samples, b.counter + 1, side));
+    LAUNCH(launch_ray_prepare(P, shard, b.he_count, b.ray_samples, b.counter + 1, packs, side));
     TRY(event_at(b, ev++, e_rays));
     CUDA_TRY(cudaEventRecord(e_rays, side));
   }
@@ -495,7 +504,7 @@ static int builder_enqueue(Builder &b) {
   TRY(stage_begin(b, "first_order"));
   FirstOrderOut rayleigh = {b.peer_R1, 1, 0};                                         // :68,71,77
   FirstOrderOut mie_strength = {b.peer_M1, 0, 1};                                     // :69,72,78
-  LAUNCH(launch_first_order(P, shard, b.he_count, rayleigh, mie_strength, b.counter, st));
+  LAUNCH(launch_first_order(P, shard, b.he_count, rayleigh, mie_strength, b.counter, packs, st));
   TRY(stage_end(b));
   TRY(stage_begin(b, "first_order_exchange"));
   TRY(gather(b, b.R1));
@@ -1329,7 +1338,7 @@ extern "C" int atmlut_first_order_tables(const atmlut_planet *planet, const atml
   if (out_a && d.alloc(ta, (size_t)n4)) return 1;
   if (out_b && d.alloc(tb, (size_t)n4)) return 1;
   FirstOrderOut oa = {local_out(ta), component_a, strength_a}, ob = {local_out(tb), component_b, strength_b};
-  CUDA_TRY(launch_first_order(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, g_stream));
+  CUDA_TRY(launch_first_order(P, Shard{0, 1, 1}, P.shapes.s4[0] * P.shapes.s4[1], oa, ob, nullptr, nullptr, g_stream));
   if (out_a && d.download_rgb(ta, n4, out_a)) return 1;
   if (out_b && d.download_rgb(tb, n4, out_b)) return 1;
   CUDA_TRY(cudaStreamSynchronize(g_stream));
@@ -1412,7 +1421,7 @@ extern "C" int atmlut_ray_scatter_table(const atmlut_planet *planet, const atmlu
   unsigned char *samples = nullptr;
   if (ray_scatter_uses_samples(P)) {
     if (d.alloc(samples, ray_sample_bytes(P, n_he))) return 1;
-    CUDA_TRY(launch_ray_prepare(P, Shard{0, 1, 1}, n_he, samples, nullptr, g_stream));
+    CUDA_TRY(launch_ray_prepare(P, Shard{0, 1, 1}, n_he, samples, nullptr, nullptr, g_stream));
   }
   CUDA_TRY(launch_ray_scatter(P, Shard{0, 1, 1}, n_he, samples, j, etab, local_out(o), nullptr, g_stream));
   return d.download_rgb(o, n4, out);

@@ -90,6 +90,48 @@ static __device__ void setup_view_ray(const Params &P, int h, int e, ViewSmem &v
   __syncthreads();
 }
 
+// ------------------------------------------------------------------ view rays worked out once per build
+//
+// setup_view_ray is a latency-bound prologue (one thread's index maps, `steps` double-precision exponentials, a
+// strided integral per outer sample): inside the first-order kernel it kept a CTA's eight warps off the MUFU pipe for
+// 17 % of the kernel's time (ncu source view, profiles/r2).  k_view_prepare runs it once per pair in small CTAs -- all
+// pairs in flight together -- and leaves a compact image of ViewSmem in global memory; the consumers read it back with a
+// few coalesced loads.  Layout per pair: ViewRay (64 bytes reserved), then pkx, pky, rk2 (steps doubles each), then cv0,
+// cv1, dens0, dens1 (steps floats each).
+__host__ __device__ inline size_t view_pack_bytes(int steps) { return 64 + (size_t)steps * (3 * sizeof(double) + 4 * sizeof(float)); }
+
+__device__ __forceinline__ void store_view_ray(const ViewSmem &vs, int steps, unsigned char *pack) {
+  if (threadIdx.x == 0) *reinterpret_cast<ViewRay *>(pack) = vs.ray;
+  double *d = reinterpret_cast<double *>(pack + 64);
+  float *f = reinterpret_cast<float *>(pack + 64 + (size_t)steps * 3 * sizeof(double));
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    d[k] = vs.pkx[k];
+    d[steps + k] = vs.pky[k];
+    d[2 * steps + k] = vs.rk2[k];
+    f[k] = vs.cv0[k];
+    f[steps + k] = vs.cv1[k];
+    f[2 * steps + k] = vs.dens0[k];
+    f[3 * steps + k] = vs.dens1[k];
+  }
+}
+
+// ends with a CTA barrier, like setup_view_ray
+__device__ __forceinline__ void load_view_ray(ViewSmem &vs, int steps, const unsigned char *__restrict__ pack) {
+  if (threadIdx.x == 0) vs.ray = *reinterpret_cast<const ViewRay *>(pack);
+  const double *d = reinterpret_cast<const double *>(pack + 64);
+  const float *f = reinterpret_cast<const float *>(pack + 64 + (size_t)steps * 3 * sizeof(double));
+  for (int k = threadIdx.x; k < steps; k += blockDim.x) {
+    vs.pkx[k] = __ldg(d + k);
+    vs.pky[k] = __ldg(d + steps + k);
+    vs.rk2[k] = __ldg(d + 2 * steps + k);
+    vs.cv0[k] = __ldg(f + k);
+    vs.cv1[k] = __ldg(f + steps + k);
+    vs.dens0[k] = __ldg(f + 2 * steps + k);
+    vs.dens1[k] = __ldg(f + 3 * steps + k);
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void store_all(const PeerOut &o, size_t idx, float4 v) {
 #pragma unroll 1
   for (int q = 0; q < o.n; q++) o.p[q][idx] = v;

@@ -428,7 +428,7 @@ struct alignas(16) RaySample {
 // step 00<->01, 10<->11; the swaps commute, so the slot of role r at sample k is r xor the parity of the steps so
 // far).  Offsets and weights are therefore stored in slot order, with a mask of the slots to load.
 __global__ void __launch_bounds__(256) k_ray_prepare(Params P, Shard shard, RaySample *__restrict__ samples,
-                                                     unsigned long long *counter) {
+                                                     unsigned long long *counter, const unsigned char *view_packs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned char s_code[kMaxSteps];
   __shared__ unsigned char s_mask[kMaxSteps];
@@ -441,7 +441,10 @@ __global__ void __launch_bounds__(256) k_ray_prepare(Params P, Shard shard, RayS
   const int h = he / E, e = he % E;
   const int tid = threadIdx.x;
   unsigned esamples = 0;
-  setup_view_ray(P, h, e, vs, esamples);
+  if (view_packs)
+    load_view_ray(vs, steps, view_packs + (size_t)he * view_pack_bytes(steps));
+  else
+    setup_view_ray(P, h, e, vs, esamples);
   const ViewRay ray = vs.ray;
   const V3 v = v3(ray.vx, ray.vy, 0.0);
   const float a = (float)(ray.dlen / (double)steps);      // ray.clj:19-30: stepsize * |direction|
@@ -951,12 +954,12 @@ size_t ray_sample_bytes(const Params &P, int he_count) {
 }
 
 cudaError_t launch_ray_prepare(const Params &P, Shard shard, int he_count, void *samples, unsigned long long *counter,
-                               cudaStream_t st) {
+                               const void *view_packs, cudaStream_t st) {
   if (he_count <= 0 || !ray_scatter_uses_samples(P)) return cudaSuccess;
   const size_t smem = sizeof(ViewSmem) + (size_t)P.shapes.ray_steps * sizeof(RaySample);
   cudaError_t e = cudaFuncSetAttribute(k_ray_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_ray_prepare<<<he_count, 256, smem, st>>>(P, shard, (RaySample *)samples, counter);
+  k_ray_prepare<<<he_count, 256, smem, st>>>(P, shard, (RaySample *)samples, counter, (const unsigned char *)view_packs);
   return cudaGetLastError();
 }
 

@@ -136,9 +136,20 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
+// The view rays of a shard's pairs, once per build (see atm_kernel_common.cuh): slot = the pair's global index.
+__global__ void __launch_bounds__(64) k_view_prepare(Params P, Shard shard, unsigned char *packs, unsigned long long *counter) {
+  __shared__ ViewSmem vs;
+  const int he = shard_pair(shard, blockIdx.x);
+  const int E = P.shapes.s4[1];
+  unsigned esamples = 0;
+  setup_view_ray(P, he / E, he % E, vs, esamples);
+  store_view_ray(vs, P.shapes.ray_steps, packs + (size_t)he * view_pack_bytes(P.shapes.ray_steps));
+  count_esamples(counter, esamples);
+}
+
 __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int he_count, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
-                                                     unsigned long long *counter) {
+                                                     unsigned long long *counter, const unsigned char *view_packs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ViewSmem &vs = *reinterpret_cast<ViewSmem *>(smem_raw);
   float *partial = reinterpret_cast<float *>(smem_raw + sizeof(ViewSmem));  // [6][blockDim] when kparts > 1
@@ -151,7 +162,10 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
-  setup_view_ray(P, h, e, vs, esamples);
+  if (view_packs)
+    load_view_ray(vs, steps, view_packs + (size_t)he * view_pack_bytes(steps));
+  else
+    setup_view_ray(P, h, e, vs, esamples);
   const ViewRay ray = vs.ray;
   const V3 v = v3(ray.vx, ray.vy, 0.0);
 
@@ -458,8 +472,19 @@ static int env_int(const char *name, int fallback) {
   return v && *v ? atoi(v) : fallback;
 }
 
+size_t view_pack_total_bytes(const Params &P) {
+  return (size_t)P.shapes.s4[0] * P.shapes.s4[1] * view_pack_bytes(P.shapes.ray_steps);
+}
+
+cudaError_t launch_view_prepare(const Params &P, Shard shard, int he_count, void *packs, unsigned long long *counter,
+                                cudaStream_t st) {
+  if (he_count <= 0) return cudaSuccess;
+  k_view_prepare<<<he_count, 64, 0, st>>>(P, shard, (unsigned char *)packs, counter);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
-                               unsigned long long *counter, cudaStream_t st) {
+                               unsigned long long *counter, const void *view_packs, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
   static const int max_warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
@@ -492,7 +517,8 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
   }
   const int threads = warps * 32;
   size_t smem = sizeof(ViewSmem) + (kparts > 1 ? 6 * threads * sizeof(float) : 0);
-  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter);
+  k_first_order<<<he_count * nchunks, threads, smem, st>>>(P, shard, he_count, kparts, passes, nchunks, oa, ob, counter,
+                                                          (const unsigned char *)view_packs);
   return cudaGetLastError();
 }
 

@@ -71,8 +71,15 @@ struct HalfDirInfo {
 
 cudaError_t launch_transmittance_table(const Params &P, float4 *out, cudaStream_t st);
 cudaError_t launch_surface_radiance_base(const Params &P, float4 *out, cudaStream_t st);
+// The view ray of every (height, elevation) pair of a shard -- outer sample points, column densities x -> p_k, densities
+// at p_k -- written once per build (view_pack_total_bytes(P) bytes, slot = global pair index) and read by the
+// first-order kernel and by launch_ray_prepare instead of working it out per CTA.  view_packs may be NULL there: the
+// kernels then integrate the view ray themselves.
+size_t view_pack_total_bytes(const Params &P);
+cudaError_t launch_view_prepare(const Params &P, Shard shard, int he_count, void *packs, unsigned long long *counter,
+                                cudaStream_t st);
 cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, FirstOrderOut oa, FirstOrderOut ob,
-                               unsigned long long *counter, cudaStream_t st);
+                               unsigned long long *counter, const void *view_packs, cudaStream_t st);
 // exp_table: device array of kExpTabSize doubles, exp(i/64) for i = kExpTabLo .. kExpTabHi (see exp_tab)
 // The ray-scatter kernel reads per-(pair, outer sample) records that do not depend on the scattering order:
 // launch_ray_prepare writes them once per build (ray_sample_bytes(P, he_count) bytes for the same shard and
@@ -80,7 +87,7 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
 bool ray_scatter_uses_samples(const Params &P);
 size_t ray_sample_bytes(const Params &P, int he_count);
 cudaError_t launch_ray_prepare(const Params &P, Shard shard, int he_count, void *samples, unsigned long long *counter,
-                               cudaStream_t st);
+                               const void *view_packs, cudaStream_t st);
 cudaError_t launch_ray_scatter(const Params &P, Shard shard, int he_count, const void *samples, const float4 *dj,
                                const double *exp_table, PeerOut out, unsigned long long *counter, cudaStream_t st);
 // cross-GPU barrier over peer-mapped flag words: signal the next epoch to every peer, wait for every peer's signal.

@@ -128,6 +128,50 @@ __global__ void k_mix(float *out, double c0, double c1, double c2, float k1, flo
   out[blockIdx.x * blockDim.x + threadIdx.x] = s1 + s2;
 }
 
+// the first-order kernel's hot loop as shipped (atm_device.cuh density_sums_seq): per PAIR of samples 2 DADD, an
+// integer repack, 2 FADD, 7 packed FFMA2 / FMUL2, 4 MUFU.EX2 and 2 FADD2 -- 19 issue slots for 4 exponentials, all lanes
+// active, no per-item prologue: the ceiling of this instruction mix
+__global__ void k_mix_packed(float *out, double u0, double step2_0, double step2_inc, float d1f0, float d1f_inc, float k0,
+                             float k1, float b0, float b1) {
+  float2 acc0a = make_float2(0.f, 0.f), acc1a = make_float2(0.f, 0.f), acc0b = make_float2(0.f, 0.f), acc1b = make_float2(0.f, 0.f);
+  for (int rep = 0; rep < ITERS / 16; rep++) {
+    double u = u0 + threadIdx.x * 1e-9 + rep * 1e-9, step2 = step2_0;
+    float d1f = d1f0;
+#pragma unroll 4
+    for (int j = 0; j < 128; j += 4) {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        int hi = __double2hiint(u), lo = __double2loint(u);
+        const float ue = __int_as_float(__funnelshift_l(lo, hi - 0x38000000, 3));
+        const float2 uu = make_float2(ue, ue + d1f);
+        float2 q = __ffma2_rn(uu, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
+        q = __ffma2_rn(q, uu, make_float2(0.0625f, 0.0625f));
+        q = __ffma2_rn(q, uu, make_float2(-0.125f, -0.125f));
+        q = __ffma2_rn(q, uu, make_float2(0.5f, 0.5f));
+        const float2 hq = __fmul2_rn(uu, q);
+        const float2 a0 = __ffma2_rn(hq, make_float2(k0, k0), make_float2(b0, b0));
+        const float2 a1 = __ffma2_rn(hq, make_float2(k1, k1), make_float2(b1, b1));
+        float2 e0, e1;
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0.x) : "f"(a0.x));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0.y) : "f"(a0.y));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1.x) : "f"(a1.x));
+        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1.y) : "f"(a1.y));
+        if (half == 0) {
+          acc0a = __fadd2_rn(acc0a, e0);
+          acc1a = __fadd2_rn(acc1a, e1);
+        } else {
+          acc0b = __fadd2_rn(acc0b, e0);
+          acc1b = __fadd2_rn(acc1b, e1);
+        }
+        u += step2;
+        step2 += step2_inc;
+        d1f += d1f_inc;
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (acc0a.x + acc0a.y) + (acc1a.x + acc1a.y) + (acc0b.x + acc0b.y) + (acc1b.x + acc1b.y);
+}
+
 template <typename F>
 static double time_ms(F launch) {
   cudaEvent_t a, b;
@@ -162,15 +206,20 @@ int main() {
   double t_rsq = time_ms([&] { k_rsqrt<<<blocks, threads>>>((float *)buf, 1.0f); });
   double t_cvt = time_ms([&] { k_cvt<<<blocks, threads>>>((float *)buf, 1.5); });
   double t_mix = time_ms([&] { k_mix<<<blocks, threads>>>((float *)buf, 1e-3, 1e-7, 1e-12, -3.0f, -20.0f); });
+  // 4 CTAs of 256 threads per SM like the shipped kernel (64 registers); ITERS / 16 * 128 samples per thread
+  double t_mixp = time_ms([&] { k_mix_packed<<<sms * 4 * 4, threads>>>((float *)buf, 1e-3, 2e-6, 1e-9, 1e-6f, 1e-9f, -300.f, -2000.f, 0.1f, 0.7f); });
+  double n_mixp = (double)sms * 16 * threads * (ITERS / 16) * 128;
+  // the same with 48 KB of (unused) dynamic shared memory per CTA: 4 resident CTAs = 32 warps per SM, the shipped occupancy
+  double t_mixp4 = time_ms([&] { k_mix_packed<<<sms * 4 * 4, threads, 48 * 1024>>>((float *)buf, 1e-3, 2e-6, 1e-9, 1e-6f, 1e-9f, -300.f, -2000.f, 0.1f, 0.7f); });
   CHECK(cudaGetLastError());
   int clk = 0;
   cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, "
          "\"ffma_per_s\": %.4e, \"dfma_per_s\": %.4e, \"mufu_ex2_per_s\": %.4e, \"mufu_rsqrt_per_s\": %.4e, "
-         "\"cvt_f64_f32_loop_per_s\": %.4e, \"mixed_esample_per_s\": %.4e, "
+         "\"cvt_f64_f32_loop_per_s\": %.4e, \"mixed_esample_per_s\": %.4e, \"packed_hot_loop_exp_per_s\": %.4e, \"packed_hot_loop_exp_per_s_32_warps\": %.4e, "
          "\"ffma_per_clk_sm\": %.2f, \"dfma_per_clk_sm\": %.2f, \"ex2_per_clk_sm\": %.2f}\n",
          p.name, sms, clk, n / (t_ffma * 1e-3), n / (t_dfma * 1e-3), n / (t_ex2 * 1e-3), n / (t_rsq * 1e-3),
-         n / (t_cvt * 1e-3), n / (t_mix * 1e-3), n / (t_ffma * 1e-3) / (clk * 1e3) / sms,
+         n / (t_cvt * 1e-3), n / (t_mix * 1e-3), 2 * n_mixp / (t_mixp * 1e-3), 2 * n_mixp / (t_mixp4 * 1e-3), n / (t_ffma * 1e-3) / (clk * 1e3) / sms,
          n / (t_dfma * 1e-3) / (clk * 1e3) / sms, n / (t_ex2 * 1e-3) / (clk * 1e3) / sms);
   return 0;
 }
