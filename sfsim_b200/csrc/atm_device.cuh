@@ -89,26 +89,6 @@ __device__ __forceinline__ void densities_general(const Params &P, double rq2, f
   e1 = (float)exp(-(h / P.medium.scale[1]));
 }
 
-// Sum over samples j = j0, j0 + stride, ... < steps of exp(-h(q_j)/scale_c).
-// Strided variant (used with one warp per segment): direct Horner evaluation per sample.
-__device__ __forceinline__ void density_sums_strided(const Params &P, const Quad &q, int steps, int j0, int stride,
-                                                     float &s0, float &s1, unsigned &count) {
-  s0 = 0.f;
-  s1 = 0.f;
-  for (int j = j0; j < steps; j += stride) {
-    double m = (double)j + 0.5;
-    double u = fma(fma(q.C, m, q.B), m, q.A);
-    float e0, e1;
-    if (P.fast.poly)
-      densities_from_u(P.fast, trunc_d2f(u), e0, e1);
-    else
-      densities_general(P, fma(u, P.fast.rp2, P.fast.rp2), e0, e1);
-    s0 += e0;
-    s1 += e1;
-    count++;
-  }
-}
-
 // exp(-h/scale_c) of TWO samples at once with Blackwell's packed FP32 instructions (FFMA2 / FMUL2:
 // one issue slot for two lanes of work).  The loop is co-limited by issue slots and the MUFU pipe; packing
 // the polynomial takes it off the issue limit.

@@ -137,7 +137,7 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
 // while each group stays a coherent row block (no extra divergence).
 // kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
 // The view rays of a shard's pairs, once per build (see atm_kernel_common.cuh): slot = the pair's global index.
-__global__ void __launch_bounds__(64) k_view_prepare(Params P, Shard shard, unsigned char *packs, unsigned long long *counter) {
+__global__ void __launch_bounds__(128) k_view_prepare(Params P, Shard shard, unsigned char *packs, unsigned long long *counter) {
   __shared__ ViewSmem vs;
   const int he = shard_pair(shard, blockIdx.x);
   const int E = P.shapes.s4[1];
@@ -479,7 +479,7 @@ size_t view_pack_total_bytes(const Params &P) {
 cudaError_t launch_view_prepare(const Params &P, Shard shard, int he_count, void *packs, unsigned long long *counter,
                                 cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
-  k_view_prepare<<<he_count, 64, 0, st>>>(P, shard, (unsigned char *)packs, counter);
+  k_view_prepare<<<he_count, 128, 0, st>>>(P, shard, (unsigned char *)packs, counter);
   return cudaGetLastError();
 }
 

@@ -14,4 +14,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ra
 # k_point_scatter_prepare matches the same expression: 1 + 5 launches per build, skip into the second build's pass 3
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_point_scatter -s 9 -c 1 -f \
     -o gpurun_out/${tag}_k_point_scatter python tools/profile_run.py > gpurun_out/${tag}_ncu_k_point_scatter.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_cube_color -s 1 -c 1 -f \
+    -o gpurun_out/${tag}_k_cube_color python tools/cubemap_run.py 4 2 > gpurun_out/${tag}_ncu_k_cube_color.log 2>&1
 ls -la gpurun_out/${tag}_*.ncu-rep

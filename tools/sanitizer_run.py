@@ -1,5 +1,5 @@
 """Small builds for compute-sanitizer (memcheck / racecheck): reduced tables with and without graph replay, the
-kparts > 1 path, wide tiles, plus the batch evaluators."""
+kparts > 1 path, wide tiles, the batch evaluators, and cube-map tiles (batch call and the streamed level)."""
 import os
 import sys
 
@@ -8,7 +8,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sfsim_b200 import _lib, atmosphere, atmosphere_lut, interpolate  # noqa: E402
 
-which = sys.argv[1:] or ["reduced", "small", "tiny", "wide", "batch"]
+which = sys.argv[1:] or ["reduced", "small", "tiny", "wide", "batch", "cubemap"]
 if "reduced" in which:   # BASELINE.json configs[0] shapes, fewer steps
     cfg = _lib.make_config(ray_scatter_shape=(8, 31, 8, 2), transmittance_shape=(16, 63), surface_radiance_shape=(4, 15),
                            ray_steps=20, sphere_steps=15, iterations=3)
@@ -35,3 +35,20 @@ if "batch" in which:
     e = interpolate.interpolation_table(np.zeros((3, 5, 3), np.float32), atmosphere.surface_radiance_space(earth, (3, 5)))
     print(atmosphere.point_scatter(earth, sc, tab, e, (1, 1, 1), 6, 8, (6379000.0, 0, 0), (0, 1, 0), (0.6, 0.8, 0)))
     print(atmosphere.surface_radiance(earth, tab, 8, (6379000.0, 0, 0), (0.6, 0.8, 0)))
+if "cubemap" in which:
+    from oracle import cubemap as ocm                   # synthetic rasters only
+    from sfsim_b200 import cubemap
+    width = 16
+    elev, day, night = ocm.synthetic_world(width, [0, 1], [1], seed=3)
+    w = cubemap.World(width)
+    for level in (0, 1):
+        w.set_elevation(level, elev[level])
+    w.set_color(False, 1, day[1])
+    w.set_color(True, 1, night[1])
+    cfg = cubemap.make_config(0, 1, width=width, surface_tilesize=9)
+    out = w.make_cube_map_tiles(cfg, cubemap.tile_shard(1))
+    seen = []
+    w.make_cube_map(0, 1, lambda key, tile: seen.append(int(tile["day"][0, 0, 0])), batch=5, surface_tilesize=9)
+    print("cubemap", out["day"].shape, len(seen), float(np.abs(out["surface"]).max()),
+          w.project_onto_globe([(1.0, 2.0, 3.0)], 1).tolist(), flush=True)
+    w.close()
