@@ -517,15 +517,23 @@ def run_b200(args):
         roofline = None
         if first_ms and work.get("esamples_first_order") and mufu_peak:
             achieved = 2.0 * work["esamples_first_order"] / (first_ms * 1e-3)
+            issued = work.get("mufu_ex2_per_esample") or 2.0
             roofline = {"bound": "sfu", "kernel": "k_first_order", "achieved": achieved / 1e9, "peak": mufu_peak / 1e9,
                         "unit": "G exp/s (MUFU.EX2 peak)", "frac": achieved / mufu_peak, "traffic": traffic,
                         "traffic_source": traffic_source,
+                        "mufu_ex2_issued_per_esample": issued,
+                        "mufu_pipe_frac": achieved * issued / 2.0 / mufu_peak,
                         "hbm": {"algorithmic_bytes": 2 * n4 // world * 16,
                                 "achieved_GBs": 2 * n4 / world * 16 / (first_ms * 1e-3) / 1e9, "peak_GBs": hbm_peak,
-                                "note": "two float4 output tables per launch; the kernel is SFU-bound, not HBM-bound"},
+                                "note": "two float4 output tables per launch; the kernel is SFU/FMA-bound, not HBM-bound"},
                         "peak_source": "measured on this pool's B200 by tools/pipe_peaks.cu (profiles/pipe_peaks_b200.json)",
-                        "algorithmic_units": "2 exponentials per overall-extinction sample (one per scatter component); "
-                                             "samples counted on the device, every one of them on the MUFU pipe",
+                        "algorithmic_units": "2 exponentials per overall-extinction sample (one per scatter component, "
+                                             "SURVEY.md section 8d); samples counted on the device.  `frac` is that "
+                                             "algorithmic rate against the MUFU.EX2 peak; the kernel ISSUES "
+                                             "mufu_ex2_issued_per_esample exponentials per sample (Earth's scale heights "
+                                             "are 24000 m / 20 and / 3, so every second pair of samples takes both "
+                                             "densities from one exponential as t^20 and t^3 on the FMA pipe): "
+                                             "`mufu_pipe_frac` is the MUFU pipe's own utilisation by these exponentials",
                         "esamples_per_launch": work["esamples_first_order"], "launch_ms": first_ms}
         # ray-scatter from the dJ table: bound by shared-memory wavefronts.  Floor per 4-D lookup of one warp:
         # 4 x LDS.128 (16 wavefronts) for the bilinear corners + 1 x STS.128 (4) for its share of the blended tile.

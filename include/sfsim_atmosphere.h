@@ -125,7 +125,9 @@ int atmlut_builder_stage_ms(void *builder, int stage, float *ms);
 /* sample counts of the last run: overall-extinction evaluations, 4-D lookups, 2-D lookups */
 int atmlut_builder_work(void *builder, double *esamples, double *lookups4d, double *lookups2d);
 /* which: 0 = overall-extinction samples of the first-order kernel, 1 = of the ray-scatter kernels (all
- * iterations), both counted on the device for this rank's slab; 2 = kernels launched by the last run */
+ * iterations), both counted on the device for this rank's slab; 2 = kernels launched by the last run; 3 = MUFU.EX2
+ * instructions the sampler issues per overall-extinction sample (2 exponentials each: 2, or 1.5 / 1 where the two scale
+ * heights are commensurable and both densities come from one exponential) */
 int atmlut_builder_counter(void *builder, int which, double *value);
 int atmlut_builder_destroy(void *builder);
 

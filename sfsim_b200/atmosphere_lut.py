@@ -166,7 +166,7 @@ class AtmosphereLutBuilder:
         e, l4, l2 = C.c_double(), C.c_double(), C.c_double()
         check(self.lib.atmlut_builder_work(self.handle, C.byref(e), C.byref(l4), C.byref(l2)))
         res = {"esamples": e.value, "lookups4d": l4.value, "lookups2d": l2.value}
-        for which, key in enumerate(("esamples_first_order", "esamples_ray_scatter", "kernel_launches")):
+        for which, key in enumerate(("esamples_first_order", "esamples_ray_scatter", "kernel_launches", "mufu_ex2_per_esample")):
             v = C.c_double()
             check(self.lib.atmlut_builder_counter(self.handle, which, C.byref(v)))
             res[key] = v.value

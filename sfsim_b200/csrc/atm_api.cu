@@ -92,6 +92,26 @@ int make_planet_medium(const atmlut_planet *planet, const atmlut_scatter *scatte
     P.fast.b[c] = (float)(delta * log2e / P.medium.scale[c]);
     for (int i = 0; i < 3; i++) P.fast.ext[c][i] = (float)(P.medium.base[c][i] / P.medium.quotient[c]);
   }
+  // Sampler variants (atm_device.cuh).  Degree of the height series: the u^3 term of sqrt(1+u) - 1 is 0.078 u^3 of the
+  // height; it is dropped where it moves the largest exponent (top of the atmosphere, shortest scale height) by < 4e-6.
+  // Scale heights in the ratio 3 : 20 (exactly, in double): one exponential per sample on every second pair.
+  static const int knob_pow = getenv("ATMLUT_POW") ? atoi(getenv("ATMLUT_POW")) : 2;       // A/B: 0 off, 1 every pair, 2 alternate
+  static const int knob_degree = getenv("ATMLUT_DEGREE") ? atoi(getenv("ATMLUT_DEGREE")) : 0;   // A/B: 0 automatic
+  const double u_max = (Rt * Rt - Rp * Rp) / (Rp * Rp);
+  const double min_scale = n == 2 ? std::min(P.medium.scale[0], P.medium.scale[1]) : P.medium.scale[0];
+  const bool thin = 0.078 * u_max * u_max * u_max * ((Rt - R) / min_scale) < 4e-6;
+  P.fast.degree = knob_degree == 2 || knob_degree == 4 ? knob_degree : (thin ? 2 : 4);
+  P.fast.pow_mode = 0;
+  P.fast.pow_alt = knob_pow == 2 ? 1 : 0;
+  if (n == 2 && knob_pow != 0 && P.fast.degree == 2) {
+    const double s0 = P.medium.scale[0], s1 = P.medium.scale[1];
+    const double common = s0 * 20.0 == s1 * 3.0 ? s0 * 20.0 : (s0 * 3.0 == s1 * 20.0 ? s0 * 3.0 : 0.0);
+    if (common > 0.0) {
+      P.fast.pow_mode = s0 * 20.0 == s1 * 3.0 ? 1 : 2;
+      P.fast.kt = (float)(-Rp * log2e / common);
+      P.fast.bt = (float)(delta * log2e / common);
+    }
+  }
   for (int i = 0; i < 3; i++) P.intensity[i] = 1.0;
   return 0;
 }
@@ -1051,7 +1071,12 @@ extern "C" int atmlut_builder_counter(void *builder, int which, double *value) {
     *value = (double)b->launches;
     return 0;
   }
-  if (which < 0 || which > 2) return fail("which must be 0, 1 or 2");
+  if (which == 3) {   // MUFU.EX2 instructions per overall-extinction sample of the fast sampler (atm_device.cuh)
+    const Fast &f = b->P.fast;
+    *value = !f.poly ? 0.0 : (f.pow_mode && f.degree == 2 ? (f.pow_alt ? 1.5 : 1.0) : 2.0);
+    return 0;
+  }
+  if (which < 0 || which > 3) return fail("which must be 0, 1, 2 or 3");
   CUDA_TRY(cudaSetDevice(b->device));
   unsigned long long c[2];
   CUDA_TRY(cudaMemcpyAsync(c, b->counter, sizeof c, cudaMemcpyDeviceToHost, b->main));

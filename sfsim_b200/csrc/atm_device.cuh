@@ -32,6 +32,18 @@ struct Fast {
   float k[2];        // -R' * log2(e) / scale_c     (exponent slope in units of h'/R')
   float b[2];        // delta * log2(e) / scale_c   (exponent offset)
   float ext[2][3];   // extinction at h = 0: base_c / quotient_c
+  // Commensurable scale heights (Earth: 1200 m and 8000 m = 24000 m / 20 and / 3): both densities are integer powers
+  // of ONE exponential t = exp(-h / 24000 m), t^20 and t^3 -- six packed multiplies on the FMA pipe instead of a
+  // second MUFU.EX2, the pipe the first-order kernel is bound by.  pow_mode 1: component 0 = t^20, component 1 = t^3;
+  // 2: the other way round; 0: scale heights in no such ratio, two exponentials.
+  int pow_mode;
+  float kt, bt;      // exponent slope and offset of t, like k[] and b[]
+  // pow_alt 1: only every second pair of samples takes the one-exponential form, which balances the MUFU and the FMA pipe
+  // (tools/pipe_peaks.cu: 35.7 clocks per pair with two exponentials, 31.0 with one, 29.7 alternating).
+  int pow_alt;
+  // degree of the series of sqrt(1+u) - 1 in u: 2 where the atmosphere is so thin against the radius that the u^3 term
+  // moves no exponent by more than 4e-6 (Earth: u <= 0.0115), else 4
+  int degree;
 };
 
 struct Params {
@@ -57,14 +69,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // exp(-h/scale_c) for both components from u = (|q|^2 - R'^2) / R'^2  (fast path, u > 0 small)
 // sqrt(1+u) - 1 = u (1/2 - u/8 + u^2/16 - 5u^3/128 + 7u^4/256 - ...)
-__device__ __forceinline__ void densities_from_u(const Fast &f, float u, float &e0, float &e1) {
-  float q = fmaf(u, 0.02734375f, -0.0390625f);
-  q = fmaf(q, u, 0.0625f);
-  q = fmaf(q, u, -0.125f);
+// ONE: both densities as powers of one exponential (component 0 = t^20, component 1 = t^3; the caller swaps for the
+// other order); k0 .. b1: exponent slopes and offsets of the two-exponential form.
+template <bool ONE, int DEG>
+__device__ __forceinline__ void densities_from_u(const Fast &f, float k0, float b0, float k1, float b1, float u, float &e0,
+                                                 float &e1) {
+  float q;
+  if (DEG == 2) {
+    q = fmaf(u, 0.0625f, -0.125f);
+  } else {
+    q = fmaf(u, 0.02734375f, -0.0390625f);
+    q = fmaf(q, u, 0.0625f);
+    q = fmaf(q, u, -0.125f);
+  }
   q = fmaf(q, u, 0.5f);
   float hq = u * q;  // h' / R'
-  e0 = ex2_approx(fmaf(hq, f.k[0], f.b[0]));
-  e1 = ex2_approx(fmaf(hq, f.k[1], f.b[1]));
+  if (!ONE) {
+    e0 = ex2_approx(fmaf(hq, k0, b0));
+    e1 = ex2_approx(fmaf(hq, k1, b1));
+  } else {
+    const float t = ex2_approx(fmaf(hq, f.kt, f.bt));
+    const float p2 = t * t, p4 = p2 * p2, p8 = p4 * p4, p16 = p8 * p8;
+    e0 = p4 * p16;
+    e1 = t * p2;
+  }
 }
 
 // Coefficients of u(m) = A + B m + C m^2, m = j + 1/2, for the samples q_j = o + dir (j + 1/2) / steps
@@ -89,69 +117,102 @@ __device__ __forceinline__ void densities_general(const Params &P, double rq2, f
   e1 = (float)exp(-(h / P.medium.scale[1]));
 }
 
-// exp(-h/scale_c) of TWO samples at once with Blackwell's packed FP32 instructions (FFMA2 / FMUL2:
-// one issue slot for two lanes of work).  The loop is co-limited by issue slots and the MUFU pipe; packing
-// the polynomial takes it off the issue limit.
-__device__ __forceinline__ void densities_from_u2(const Fast &f, float2 u, float2 &e0, float2 &e1) {
-  float2 q = __ffma2_rn(u, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
-  q = __ffma2_rn(q, u, make_float2(0.0625f, 0.0625f));
-  q = __ffma2_rn(q, u, make_float2(-0.125f, -0.125f));
+// acc_c += exp(-h/scale_c) for TWO samples at once with Blackwell's packed FP32 instructions (FFMA2 / FMUL2: one issue
+// slot for two lanes of work).  Two exponentials per sample: four MUFU.EX2 per pair; ONE: two, and the powers
+// t^3 = t t^2 and t^20 = t^4 t^16 fused with the accumulation (six packed instructions).
+template <bool ONE, int DEG>
+__device__ __forceinline__ void accumulate_densities2(const Fast &f, float k0, float b0, float k1, float b1, float2 u,
+                                                      float2 &acc0, float2 &acc1) {
+  float2 q;
+  if (DEG == 2) {
+    q = __ffma2_rn(u, make_float2(0.0625f, 0.0625f), make_float2(-0.125f, -0.125f));
+  } else {
+    q = __ffma2_rn(u, make_float2(0.02734375f, 0.02734375f), make_float2(-0.0390625f, -0.0390625f));
+    q = __ffma2_rn(q, u, make_float2(0.0625f, 0.0625f));
+    q = __ffma2_rn(q, u, make_float2(-0.125f, -0.125f));
+  }
   q = __ffma2_rn(q, u, make_float2(0.5f, 0.5f));
   const float2 hq = __fmul2_rn(u, q);  // h' / R'
-  const float2 a0 = __ffma2_rn(hq, make_float2(f.k[0], f.k[0]), make_float2(f.b[0], f.b[0]));
-  const float2 a1 = __ffma2_rn(hq, make_float2(f.k[1], f.k[1]), make_float2(f.b[1], f.b[1]));
-  e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
-  e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+  if (!ONE) {
+    const float2 a0 = __ffma2_rn(hq, make_float2(k0, k0), make_float2(b0, b0));
+    const float2 a1 = __ffma2_rn(hq, make_float2(k1, k1), make_float2(b1, b1));
+    acc0 = __fadd2_rn(acc0, make_float2(ex2_approx(a0.x), ex2_approx(a0.y)));
+    acc1 = __fadd2_rn(acc1, make_float2(ex2_approx(a1.x), ex2_approx(a1.y)));
+  } else {
+    const float2 a = __ffma2_rn(hq, make_float2(f.kt, f.kt), make_float2(f.bt, f.bt));
+    const float2 t = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    const float2 p2 = __fmul2_rn(t, t);
+    const float2 p4 = __fmul2_rn(p2, p2);
+    const float2 p8 = __fmul2_rn(p4, p4);
+    const float2 p16 = __fmul2_rn(p8, p8);
+    acc0 = __ffma2_rn(p4, p16, acc0);
+    acc1 = __ffma2_rn(t, p2, acc1);
+  }
 }
 
-// Sequential variant (one thread per segment): u(m) advances by forward differences in double, two
-// samples per step (2 DADD per pair); the odd sample's u is the even one's float image plus the float
-// first difference.  Packed accumulators, two independent pairs in flight.
-__device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
-  if (P.fast.poly) {
-    double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // u at m = 1/2
-    const double d1 = q.B + 2.0 * q.C;               // u(m+1) - u(m) at m = 1/2
-    const double d2 = 2.0 * q.C;                     // second difference
-    double step2 = 2.0 * d1 + d2;                    // u(m+2) - u(m)
-    const double step2_inc = 4.0 * d2;
-    float d1f = (float)d1;                           // first difference at the even sample, in float
-    const float d1f_inc = (float)(2.0 * d2);
-    float2 acc0a = make_float2(0.f, 0.f), acc1a = make_float2(0.f, 0.f);
-    float2 acc0b = make_float2(0.f, 0.f), acc1b = make_float2(0.f, 0.f);
-    int j = 0;
+// Sum over the `steps` samples of a segment of exp(-h(q_j)/scale_c), one thread per segment: u(m) advances by forward
+// differences in double, four samples per step (2 DADD); the other three u are the float image of the first plus float
+// differences.  Packed accumulators, two independent pairs in flight (pair A: ONE_A, pair B: ONE_B).
+// `swap`: the one-exponential form yields (t^20, t^3); the medium lists its components the other way round.
+template <bool ONE_A, bool ONE_B, int DEG>
+__device__ __forceinline__ void density_sums_fast(const Fast &f, bool swap, const Quad &q, int steps, float &s0, float &s1) {
+  const float k0 = f.k[swap ? 1 : 0], b0 = f.b[swap ? 1 : 0], k1 = f.k[swap ? 0 : 1], b1 = f.b[swap ? 0 : 1];
+  double u = fma(fma(q.C, 0.5, q.B), 0.5, q.A);   // u at m = 1/2
+  const double d1 = q.B + 2.0 * q.C;               // u(m+1) - u(m) at m = 1/2
+  const double d2 = 2.0 * q.C;                     // second difference
+  // four samples per trip: u(m) in double (2 DADD per trip), u(m+1..3) = its float image plus float differences
+  // e_i(m) = u(m+i) - u(m) = i d1(m) + (i (i-1) / 2) d2, which grow by 4 i d2 per trip
+  double step4 = 4.0 * d1 + 6.0 * d2;              // u(m+4) - u(m)
+  const double step4_inc = 16.0 * d2;
+  float e1 = (float)d1;
+  float2 e23 = make_float2((float)(2.0 * d1 + d2), (float)(3.0 * d1 + 3.0 * d2));
+  const float e1_inc = (float)(4.0 * d2);
+  const float2 e23_inc = make_float2((float)(8.0 * d2), (float)(12.0 * d2));
+  float2 acc0a = make_float2(0.f, 0.f), acc1a = make_float2(0.f, 0.f);
+  float2 acc0b = make_float2(0.f, 0.f), acc1b = make_float2(0.f, 0.f);
+  int j = 0;
 #pragma unroll kSamplerUnroll
-    for (; j + 4 <= steps; j += 4) {
-      float2 e0, e1;
-      float ue = trunc_d2f(u);
-      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
-      acc0a = __fadd2_rn(acc0a, e0);
-      acc1a = __fadd2_rn(acc1a, e1);
-      u += step2;
-      step2 += step2_inc;
-      d1f += d1f_inc;
-      ue = trunc_d2f(u);
-      densities_from_u2(P.fast, make_float2(ue, ue + d1f), e0, e1);
-      acc0b = __fadd2_rn(acc0b, e0);
-      acc1b = __fadd2_rn(acc1b, e1);
-      u += step2;
-      step2 += step2_inc;
-      d1f += d1f_inc;
+  for (; j + 4 <= steps; j += 4) {
+    const float ue = trunc_d2f(u);
+    accumulate_densities2<ONE_A, DEG>(f, k0, b0, k1, b1, make_float2(ue, ue + e1), acc0a, acc1a);
+    accumulate_densities2<ONE_B, DEG>(f, k0, b0, k1, b1, __fadd2_rn(make_float2(ue, ue), e23), acc0b, acc1b);
+    u += step4;
+    step4 += step4_inc;
+    e1 += e1_inc;
+    e23 = __fadd2_rn(e23, e23_inc);
+  }
+  float t0 = 0.f, t1 = 0.f;
+  if (j < steps) {
+    // tail of up to 3 samples, one at a time: u(m+1) = u(m) + d1(m)
+    double d1m = d1 + (double)j * d2;
+    for (; j < steps; j++) {
+      float x0, x1;
+      densities_from_u<ONE_B, DEG>(f, k0, b0, k1, b1, trunc_d2f(u), x0, x1);
+      t0 += x0;
+      t1 += x1;
+      u += d1m;
+      d1m += d2;
     }
-    float t0 = 0.f, t1 = 0.f;
-    if (j < steps) {
-      // tail of up to 3 samples, one at a time: u(m+1) = u(m) + d1(m)
-      double d1m = d1 + (double)j * d2;
-      for (; j < steps; j++) {
-        float x0, x1;
-        densities_from_u(P.fast, trunc_d2f(u), x0, x1);
-        t0 += x0;
-        t1 += x1;
-        u += d1m;
-        d1m += d2;
-      }
+  }
+  const float r0 = ((acc0a.x + acc0b.x) + (acc0a.y + acc0b.y)) + t0;
+  const float r1 = ((acc1a.x + acc1b.x) + (acc1a.y + acc1b.y)) + t1;
+  s0 = swap ? r1 : r0;
+  s1 = swap ? r0 : r1;
+}
+
+__device__ __forceinline__ void density_sums_seq(const Params &P, const Quad &q, int steps, float &s0, float &s1) {
+  const Fast &f = P.fast;
+  if (f.poly) {
+    if (f.pow_mode && f.degree == 2) {
+      if (f.pow_alt)
+        density_sums_fast<false, true, 2>(f, f.pow_mode == 2, q, steps, s0, s1);
+      else
+        density_sums_fast<true, true, 2>(f, f.pow_mode == 2, q, steps, s0, s1);
+    } else if (f.degree == 2) {
+      density_sums_fast<false, false, 2>(f, false, q, steps, s0, s1);
+    } else {
+      density_sums_fast<false, false, 4>(f, false, q, steps, s0, s1);
     }
-    s0 = ((acc0a.x + acc0b.x) + (acc0a.y + acc0b.y)) + t0;
-    s1 = ((acc1a.x + acc1b.x) + (acc1a.y + acc1b.y)) + t1;
   } else {
     s0 = 0.f;
     s1 = 0.f;

@@ -5,7 +5,10 @@ The hot loop of the CUDA kernels evaluates exp(-h/H_c) along a ray as
     uf  = float32(u)                        by truncation (bit manipulation on the device)
     h'  = R' * uf * (1/2 - uf/8 + uf^2/16 - 5 uf^3/128 + 7 uf^4/256)     in float32 (FMA chain)
     e_c = 2^(k_c * h'/R' + b_c)             MUFU.EX2 (<= 2 ulp), float32 sums, float32 optical depth
-with R' = R - R/4096.  This test replays exactly that arithmetic on the CPU (float32 numpy, FMA emulated through
+with R' = R - R/4096.  `column_shipped_model` below is the variant the library picks for the shipped Earth parameters
+(atm_device.cuh density_sums_fast<false, true, 2>): one float64 u per FOUR samples and float32 differences for the other
+three, the series cut after u^2, and on every second pair of samples both densities from ONE exponential
+t = exp(-h / 24000 m) as t^20 and t^3 (1200 m and 8000 m are 24000 m / 20 and / 3).  This test replays exactly that arithmetic on the CPU (float32 numpy, FMA emulated through
 float64) for random rays of the shipped atmosphere and compares the transmittance with the float64 reference
 formula h = |q| - R.  It pins the precision claims without a GPU: the cancellation-free form keeps the error of
 exp(-tau) below 1e-5 even at optical depth 20+, where naive float32 `|q| - R` is off by more than 1e-3.
@@ -82,6 +85,48 @@ def column_kernel_model(r0, mu, t_end):
     return cols
 
 
+def column_shipped_model(r0, mu, t_end, mufu_noise=0.0, rng=None):
+    delta = R / 4096.0
+    rp = R - delta
+    inv_rp2 = 1.0 / (rp * rp)
+    a = ((r0 ** 2 - rp * rp) * inv_rp2)[:, None]
+    b = ((2.0 * r0 * mu * t_end / STEPS) * inv_rp2)[:, None]
+    c = ((t_end ** 2 / STEPS ** 2) * inv_rp2)[:, None]
+    j = np.arange(STEPS)
+    base = (4 * (j // 4) + 0.5)[None, :]                                   # m of the group's first sample
+    i = (j % 4)[None, :].astype(np.float64)
+    u_base = trunc_to_f32(a + base * (b + base * c))                       # float64 chain, truncated
+    diff = (i * b + c * (2.0 * base * i + i * i)).astype(f32)              # u(m + i) - u(m), kept in float32
+    uf = (u_base + diff).astype(f32)
+    q = fma32(uf, np.full_like(uf, f32(0.0625)), np.full_like(uf, f32(-0.125)))
+    q = fma32(q, uf, np.full_like(uf, f32(0.5)))
+    hq = (uf * q).astype(f32)
+
+    def ex2(arg):
+        e = np.exp2(arg.astype(np.float64))
+        if mufu_noise:
+            e = e * (1.0 + rng.uniform(-mufu_noise, mufu_noise, e.shape))
+        return e.astype(f32)
+
+    two = [ex2(fma32(hq, np.full_like(hq, f32(-rp * LOG2E / s)), np.full_like(hq, f32(delta * LOG2E / s)))) for s in SCALE]
+    t = ex2(fma32(hq, np.full_like(hq, f32(-rp * LOG2E / 24000.0)), np.full_like(hq, f32(delta * LOG2E / 24000.0))))
+    p2 = (t * t).astype(f32)
+    p4 = (p2 * p2).astype(f32)
+    p8 = (p4 * p4).astype(f32)
+    p16 = (p8 * p8).astype(f32)
+    one = [(p4 * p16).astype(f32), (t * p2).astype(f32)]                   # t^20 (mie), t^3 (rayleigh)
+    second_pair = ((j % 4) >= 2)[None, :]
+    cols = []
+    for comp in range(2):
+        e = np.where(second_pair, one[comp], two[comp])
+        acc = np.zeros(len(r0), dtype=f32)
+        for k in range(STEPS):
+            acc = (acc + e[:, k]).astype(f32)
+        seg = (t_end / STEPS).astype(f32)
+        cols.append((acc * seg).astype(f32).astype(np.float64))
+    return cols
+
+
 def column_naive_f32(r0, mu, t_end):
     m = (np.arange(STEPS) + 0.5)[None, :].astype(f32)
     t = ((t_end[:, None] / STEPS).astype(f32) * m).astype(f32)
@@ -107,6 +152,20 @@ def test_kernel_sampler_model_meets_the_tolerance():
     assert tau.max() > 15.0                                   # the sample reaches the deep-twilight regime
     assert err.max() < 1e-5                                   # ten times inside the 1e-4 tolerance
     assert np.median(err) < 2e-7
+
+
+def test_shipped_sampler_variant_meets_the_tolerance():
+    """the variant picked for Earth: degree-2 series, four samples per float64 step, one exponential on every second pair;
+    MUFU.EX2 modelled as exact and with a uniform error of +-2^-22 (its documented bound)"""
+    rng = np.random.default_rng(7)
+    r0, mu, t_end = ray_samples(rng, 4000)
+    ref, tau = transmittance(column_reference(r0, mu, t_end))
+    for noise in (0.0, 2.0 ** -22):
+        got, _ = transmittance(column_shipped_model(r0, mu, t_end, noise, rng))
+        err = np.abs(got - ref) / ref
+        assert tau.max() > 15.0
+        assert err.max() < 2.5e-5                              # four times inside the 1e-4 tolerance at optical depth 20+
+        assert np.quantile(err, 0.999) < 1e-5 and np.median(err) < 2e-7
 
 
 def test_naive_float32_height_fails_the_tolerance():
