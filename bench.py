@@ -501,9 +501,10 @@ def run_b200(args):
         # DRAM traffic of one first-order launch from the committed `ncu --set full` capture (single GPU only)
         traffic, traffic_source = None, None
         if world == 1 and args.workload == "shipped":
-            for name in ("r2_ncu_summary.txt", "r1_final_ncu_summary.txt"):
+            for name in ("r2/r2_final_ncu_summary.txt", "r1_final_ncu_summary.txt"):
                 try:
-                    text = open(os.path.join(ROOT, "profiles", name)).read().split("== k_point_scatter")[0]
+                    blocks = open(os.path.join(ROOT, "profiles", name)).read().split("\n== ")
+                    text = [b for b in blocks if "k_first_order" in b.splitlines()[0]][0]
                     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
                     traffic = 0.0
                     for ln in text.splitlines():
