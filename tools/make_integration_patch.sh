@@ -1,5 +1,5 @@
 #!/bin/bash
-# Regenerates integration/sfsim.patch from the shim in integration/clj and the four one-line edits of the reference
+# Regenerates integration/sfsim.patch from the shims in integration/clj and the small edits of the reference
 # (build.clj, deps.edn, Makefile, scripts/packr-config-linux.json).  Needs the reference checkout (default
 # /root/reference).  tests/test_integration_patch.py checks that the committed patch still applies.
 set -e
@@ -12,6 +12,6 @@ for f in build.clj deps.edn Makefile scripts/packr-config-linux.json; do
   cp $REF/$f $W/b/$f
 done
 (cd $W/b && git init -q . && git apply $HERE/integration/sfsim.patch && rm -rf .git)
-cp $HERE/integration/clj/sfsim/atmosphere_cuda.clj $W/b/src/clj/sfsim/atmosphere_cuda.clj   # the shim is edited there
+cp $HERE/integration/clj/sfsim/atmosphere_cuda.clj $HERE/integration/clj/sfsim/globe_cuda.clj $W/b/src/clj/sfsim/   # the shims are edited there
 (cd $W && git diff --no-index --no-color a b || true) | sed 's@^diff --git a/a/@diff --git a/@; s@^diff --git a/b/@diff --git a/@; s@ b/b/@ b/@; s@^--- a/a/@--- a/@; s@^+++ b/b/@+++ b/@'
 rm -rf $W
