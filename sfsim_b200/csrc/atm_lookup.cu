@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
   const int my_entry = si * row_pitch + ai;
   __syncthreads();                       // the mbarrier is initialised, the exponential table is filled
   mbar_wait(full, 0);
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  float2 acc01 = make_float2(0.f, 0.f);
+  float acc2 = 0.f;
   float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
   if (active) {
     const uint4 r0 = sample[0].rows;
@@ -603,16 +604,18 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
     if (active) {
       const float4 cw = r.cw, tr = r.tr;
       next_mask = __float_as_uint(tr.w);
-      float4 b;
-      b.x = tr.x * fmaf(cw.w, c3.x, fmaf(cw.z, c2.x, fmaf(cw.y, c1.x, cw.x * c0.x)));
-      b.y = tr.y * fmaf(cw.w, c3.y, fmaf(cw.z, c2.y, fmaf(cw.y, c1.y, cw.x * c0.y)));
-      b.z = tr.z * fmaf(cw.w, c3.z, fmaf(cw.z, c2.z, fmaf(cw.y, c1.z, cw.x * c0.z)));
-      b.w = 0.0f;
+      // red and green in one packed instruction per term (FFMA2: the same two IEEE operations, one issue slot)
+      float2 brg = __fmul2_rn(make_float2(cw.x, cw.x), make_float2(c0.x, c0.y));
+      brg = __ffma2_rn(make_float2(cw.y, cw.y), make_float2(c1.x, c1.y), brg);
+      brg = __ffma2_rn(make_float2(cw.z, cw.z), make_float2(c2.x, c2.y), brg);
+      brg = __ffma2_rn(make_float2(cw.w, cw.w), make_float2(c3.x, c3.y), brg);
+      brg = __fmul2_rn(make_float2(tr.x, tr.y), brg);
+      const float bb = tr.z * fmaf(cw.w, c3.z, fmaf(cw.z, c2.z, fmaf(cw.y, c1.z, cw.x * c0.z)));
       if (kSplitTile) {
-        tiles_rg[(size_t)(k & 1) * tile_entries + my_entry] = make_float2(b.x, b.y);
-        tiles_b[(size_t)(k & 1) * tile_entries + my_entry] = b.z;
+        tiles_rg[(size_t)(k & 1) * tile_entries + my_entry] = brg;
+        tiles_b[(size_t)(k & 1) * tile_entries + my_entry] = bb;
       } else {
-        tile[my_entry] = b;
+        tile[my_entry] = make_float4(brg.x, brg.y, bb, 0.0f);
       }
     }
     __syncthreads();   // one barrier per sample: the other buffer was last read before the previous barrier
@@ -640,30 +643,30 @@ __global__ void __launch_bounds__(1024) k_ray_scatter(Params P, Shard shard, con
         fs.s = 0.0f;
       }
       const int sv = min(fs.u + 1, s_last);
-      float4 v00, v01, v10, v11;
+      float2 a00, a01, a10, a11;     // red, green of the four corners
+      float z00, z01, z10, z11;      // blue
       if (kSplitTile) {
         const float2 *g0 = tiles_rg + (size_t)(k & 1) * tile_entries + fs.u * row_pitch, *g1 = g0 + (sv - fs.u) * row_pitch;
         const float *b0 = tiles_b + (size_t)(k & 1) * tile_entries + fs.u * row_pitch, *b1 = b0 + (sv - fs.u) * row_pitch;
-        const float2 a00 = g0[aa.u], a01 = g0[aa.v], a10 = g1[aa.u], a11 = g1[aa.v];
-        v00 = make_float4(a00.x, a00.y, b0[aa.u], 0.f);
-        v01 = make_float4(a01.x, a01.y, b0[aa.v], 0.f);
-        v10 = make_float4(a10.x, a10.y, b1[aa.u], 0.f);
-        v11 = make_float4(a11.x, a11.y, b1[aa.v], 0.f);
+        a00 = g0[aa.u], a01 = g0[aa.v], a10 = g1[aa.u], a11 = g1[aa.v];
+        z00 = b0[aa.u], z01 = b0[aa.v], z10 = b1[aa.u], z11 = b1[aa.v];
       } else {
         const float4 *r0 = tile + fs.u * row_pitch, *r1 = tile + sv * row_pitch;
-        v00 = r0[aa.u];
-        v01 = r0[aa.v];
-        v10 = r1[aa.u];
-        v11 = r1[aa.v];
+        const float4 v00 = r0[aa.u], v01 = r0[aa.v], v10 = r1[aa.u], v11 = r1[aa.v];
+        a00 = make_float2(v00.x, v00.y), a01 = make_float2(v01.x, v01.y), a10 = make_float2(v10.x, v10.y);
+        a11 = make_float2(v11.x, v11.y);
+        z00 = v00.z, z01 = v01.z, z10 = v10.z, z11 = v11.z;
       }
       const float ws1 = fs.s, ws0 = 1.0f - fs.s;
       const float w00 = ws0 * wa0, w01 = ws0 * wa1, w10 = ws1 * wa0, w11 = ws1 * wa1;
-      acc0 = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, fmaf(w00, v00.x, acc0))));
-      acc1 = fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, fmaf(w00, v00.y, acc1))));
-      acc2 = fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, fmaf(w00, v00.z, acc2))));
+      acc01 = __ffma2_rn(make_float2(w00, w00), a00, acc01);
+      acc01 = __ffma2_rn(make_float2(w01, w01), a01, acc01);
+      acc01 = __ffma2_rn(make_float2(w10, w10), a10, acc01);
+      acc01 = __ffma2_rn(make_float2(w11, w11), a11, acc01);
+      acc2 = fmaf(w11, z11, fmaf(w10, z10, fmaf(w01, z01, fmaf(w00, z00, acc2))));
     }
   }
-  if (active) store_all(out, (size_t)he * ntex + tid, make_float4(acc0, acc1, acc2, 0.0f));
+  if (active) store_all(out, (size_t)he * ntex + tid, make_float4(acc01.x, acc01.y, acc2, 0.0f));
 }
 
 // ================================================================== K4, current version
