@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
   const int h = he / E, e = he % E;
   const int steps = P.shapes.ray_steps;
   unsigned esamples = 0;
+  __shared__ int s_next_group;
+  if (threadIdx.x == 0) s_next_group = 0;   // published by the barrier that ends the view-ray set-up
   if (view_packs)
     load_view_ray(vs, steps, view_packs + (size_t)he * view_pack_bytes(steps));
   else
@@ -170,9 +172,8 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
   const V3 v = v3(ray.vx, ray.vy, 0.0);
 
   if (kparts == 1) {
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int total_warps = nchunks * nwarps;            // warps serving this pair
-    const int wg = chunk * nwarps + warp;
     // Lane layout.  Whether the sun is visible from p_k depends mostly on the light-elevation row and on k, and
     // visible k form an interval.  With narrow rows (A headings, A a power of two below 32) a warp therefore takes
     // ONE row and spreads the outer samples over 32 / A lane groups, k interleaved (k = q, q + 32/A, ...): lanes
@@ -180,8 +181,16 @@ __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Param
     const bool row_layout = A < 32 && (A & (A - 1)) == 0;
     const int kq = row_layout ? 32 / A : 1;
     const int ngroups = row_layout ? S : (ntex + 31) >> 5;
-    for (int pass = 0; pass < passes; pass++) {
-      const int group = pass * total_warps + ((pass & 1) ? total_warps - 1 - wg : wg);
+    // The CTA's row groups (the same set as a static deal of `passes` groups per warp) are handed out through a counter
+    // in shared memory, the expensive high-sun rows first: a warp that finishes early takes the next group instead of
+    // idling until its CTA-mates are done (13 % of the warp slots of an SM were empty that way, ncu).
+    for (;;) {
+      int turn = 0;
+      if (lane == 0) turn = atomicAdd(&s_next_group, 1);
+      turn = __shfl_sync(0xffffffffu, turn, 0);
+      if (turn >= passes * nwarps) break;
+      const int pass = passes - 1 - turn / nwarps, slot = chunk * nwarps + turn % nwarps;
+      const int group = pass * total_warps + ((pass & 1) ? total_warps - 1 - slot : slot);
       const int texel = row_layout ? group * A + (lane & (A - 1)) : group * 32 + lane;
       if (group >= ngroups || texel >= ntex) continue;
       const int si = texel / A, ai = texel % A;
@@ -487,7 +496,7 @@ cudaError_t launch_first_order(const Params &P, Shard shard, int he_count, First
                                unsigned long long *counter, const void *view_packs, cudaStream_t st) {
   if (he_count <= 0) return cudaSuccess;
   // tuning knobs (defaults chosen on B200, see profiles/): warps per CTA and texel groups per warp
-  static const int max_warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 8)));
+  static const int max_warps = std::min(8, std::max(1, env_int("ATMLUT_FIRST_ORDER_WARPS", 4)));
   static const int want_passes = std::max(1, env_int("ATMLUT_FIRST_ORDER_PASSES", 4));
   int warps = max_warps;
   const int ntex = P.shapes.s4[2] * P.shapes.s4[3];

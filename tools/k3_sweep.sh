@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the first-order kernel's CTA shape on one GPU (ATMLUT_FIRST_ORDER_WARPS x ATMLUT_FIRST_ORDER_PASSES)
 mkdir -p gpurun_out
-for w in 8 4 2; do for p in 4 2 1; do
+for w in 8 4 2; do for p in 16 8 4; do
   ATMLUT_FIRST_ORDER_WARPS=$w ATMLUT_FIRST_ORDER_PASSES=$p timeout 300 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/k3_sweep_${w}_${p}.json 2> gpurun_out/k3_sweep_${w}_${p}.err
   python - <<PY
 import json
