@@ -129,13 +129,6 @@ __device__ __forceinline__ void first_order_store(const Params &P, const ViewRay
   }
 }
 
-// First-order ray scatter of both sources in one pass.  A (height, elevation) pair is served by `nchunks`
-// CTAs; each integrates the view ray once into shared memory (setup_view_ray) and then every warp takes
-// `passes` groups of 32 (light-elevation, heading) texels.  Texels are light-elevation major and low sun
-// rows skip most samples (sun below the local horizon), so group cost grows with the group index: groups
-// are dealt to warps in folded order (g, 2T-1-g, 2T+g, ...) so that all warps of a pair finish together
-// while each group stays a coherent row block (no extra divergence).
-// kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
 // The view rays of a shard's pairs, once per build (see atm_kernel_common.cuh): slot = the pair's global index.
 __global__ void __launch_bounds__(128) k_view_prepare(Params P, Shard shard, unsigned char *packs, unsigned long long *counter) {
   __shared__ ViewSmem vs;
@@ -147,6 +140,13 @@ __global__ void __launch_bounds__(128) k_view_prepare(Params P, Shard shard, uns
   count_esamples(counter, esamples);
 }
 
+// First-order ray scatter of both sources in one pass.  A (height, elevation) pair is served by `nchunks` CTAs; each
+// reads the pair's view ray into shared memory (load_view_ray; without packs it integrates it itself) and owns
+// `passes` x warps groups of 32 (light-elevation, heading) texels.  Texels are light-elevation major and low sun rows
+// skip most samples (sun below the local horizon), so group cost grows with the group index: the static deal folds the
+// groups over the chunks (g, 2T-1-g, 2T+g, ...) so that all CTAs of a pair get equal work, each group staying a
+// coherent row block (no extra divergence); inside a CTA the warps take groups from a counter, expensive ones first.
+// kparts > 1 (few texels per pair): one pass, the outer sample range is split over `kparts` thread groups.
 __global__ void __launch_bounds__(256, ATMLUT_FO_MIN_BLOCKS) k_first_order(Params P, Shard shard, int he_count, int kparts, int passes, int nchunks,
                                                      FirstOrderOut oa, FirstOrderOut ob,
                                                      unsigned long long *counter, const unsigned char *view_packs) {

@@ -428,3 +428,18 @@ def test_every_sampler_variant_meets_the_tolerance(name, first, second, height):
             assert float(np.max(np.abs(g64 - w64) / np.maximum(np.abs(w64), floor))) <= TOL, (name, file_name)
         else:
             assert rel_err(g, w) <= TOL, (name, file_name)
+
+
+def test_the_builder_reports_the_sampler_it_picked():
+    """atmlut_builder_counter(3): MUFU.EX2 per overall-extinction sample -- 1.5 for Earth (every second pair of samples
+    from one exponential), 2 where the scale heights are in no 3 : 20 ratio or the atmosphere is not thin"""
+    cfg = lib_config(REDUCED, iterations=0)
+    for scatter, height, want in (((atmosphere_lut.mie, atmosphere_lut.rayleigh), 35000.0, 1.5),
+                                  ((atmosphere_lut.rayleigh, atmosphere_lut.mie), 35000.0, 1.5),
+                                  ((atmosphere_lut.mie, dict(atmosphere_lut.rayleigh, scale=7994.0)), 35000.0, 2.0),
+                                  ((atmosphere_lut.mie, atmosphere_lut.rayleigh), 100000.0, 2.0)):
+        b = atmosphere_lut.AtmosphereLutBuilder(planet=dict(atmosphere_lut.earth, height=height), scatter=scatter, cfg=cfg)
+        b.run()
+        b.sync()
+        assert b.work()["mufu_ex2_per_esample"] == want
+        b.close()
