@@ -298,6 +298,15 @@ def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
     runner.barrier()
     e2e_s = (time.perf_counter() - t0) / 3
     assert delivered == len(tiles)
+    # the same call without the float normals (a host that encodes the PNG from normal_bytes): 44 % fewer bytes on the bus
+    lean = ("day", "night", "water", "surface", "normal_bytes")
+    w.time_cube_map_level(cfg, rank, world, outputs=lean)
+    runner.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        w.time_cube_map_level(cfg, rank, world, outputs=lean)
+    runner.barrier()
+    lean_s = (time.perf_counter() - t0) / 3
     res = {"workload": "cube-map tiles, output level %d (6 x %d x %d tiles, in-level %d), map tiles 675 px, cube tiles 65 / 129 "
                        "px, synthetic rasters (elevation levels %s, colour level %d)" % (
                            out_level, 1 << out_level, 1 << out_level, in_level, sorted({ls, lw}), lc),
@@ -305,7 +314,9 @@ def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
            "tiles_per_s": total_tiles / (dev_ms * 1e-3),
            "e2e": {"tiles_per_s": total_tiles / e2e_s, "seconds_per_level": e2e_s, "d2h_bytes_per_level_this_rank": d2h,
                    "h2d_bytes_per_level_this_rank": int(tiles.nbytes), "api": "sfsim_cubemap_level (batches of 256 tiles, counting "
-                   "callback)", "host_buffers": "library-owned page-locked staging, two sets"},
+                   "callback)", "host_buffers": "library-owned page-locked staging, two sets",
+                   "without_float_normals": {"tiles_per_s": total_tiles / lean_s, "seconds_per_level": lean_s,
+                                             "d2h_bytes_per_level_this_rank": (per_tile - cfg.color_tilesize ** 2 * 12) * len(tiles)}},
            "bound": "FP64 pipe / issue slots (ncu: profiles/r2/); DRAM traffic 1.2 GB per level = the outputs"}
     if with_cpu and rank == 0:
         ow = ocm.OracleWorld(675, elev, day, night)

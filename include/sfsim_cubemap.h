@@ -74,12 +74,17 @@ int sfsim_cubemap_tile_shard(int out_level, int rank, int world_size, int capaci
  * in the order of sfsim_cubemap_tile_shard.  The pointers address page-locked host memory owned by the library and are
  * valid during the call only: the callback encodes / writes the five files of the tile (globe.clj:74-78).  While the
  * callback works on one batch, the next is in flight over PCIe and the one after is being computed.  A non-zero
- * return value of `fn` aborts the level. */
+ * return value of `fn` aborts the level.  The call is bound by the bus (450 KB per tile with all six arrays): a host
+ * that encodes the normals from `normal_bytes` itself leaves SFSIM_CUBEMAP_NORMALS out and moves 44 % fewer bytes. */
+enum {   /* the arrays a level call computes, brings back and hands to the callback (the others arrive as NULL) */
+  SFSIM_CUBEMAP_DAY = 1, SFSIM_CUBEMAP_NIGHT = 2, SFSIM_CUBEMAP_WATER = 4, SFSIM_CUBEMAP_SURFACE = 8,
+  SFSIM_CUBEMAP_NORMALS = 16, SFSIM_CUBEMAP_NORMAL_BYTES = 32, SFSIM_CUBEMAP_ALL = 63
+};
 typedef int (*sfsim_cubemap_tile_fn)(void *user, int face, int b, int a, const unsigned char *day,
                                      const unsigned char *night, const unsigned char *water, const float *surface,
                                      const float *normals, const signed char *normal_bytes);
 int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg, int rank, int world_size, int batch_tiles,
-                        sfsim_cubemap_tile_fn fn, void *user);
+                        int outputs, sfsim_cubemap_tile_fn fn, void *user);
 /* a ready-made callback that reads the first and last byte of every array and counts the tiles (user = long long[2]:
  * tiles, byte sum): measures the pipeline without a consumer */
 int sfsim_cubemap_tile_counter(void *user, int face, int b, int a, const unsigned char *day, const unsigned char *night,

@@ -35,11 +35,16 @@
 (defcfn set-color-tile- "Upload one day (0) or night (1) tile" sfsim_cubemap_world_set_color_tile
   [::mem/pointer ::mem/int ::mem/int ::mem/int ::mem/int ::mem/pointer] ::mem/int)
 (defcfn level- "All tiles of one output level, each handed to the callback" sfsim_cubemap_level
-  [::mem/pointer ::mem/pointer ::mem/int ::mem/int ::mem/int
+  [::mem/pointer ::mem/pointer ::mem/int ::mem/int ::mem/int ::mem/int
    [::ffi/fn [::mem/pointer ::mem/int ::mem/int ::mem/int ::mem/pointer ::mem/pointer ::mem/pointer ::mem/pointer
               ::mem/pointer ::mem/pointer] ::mem/int]
    ::mem/pointer]
   ::mem/int)
+
+
+(def all-but-normal-bytes
+  "SFSIM_CUBEMAP_DAY | NIGHT | WATER | SURFACE | NORMALS: spit-normals encodes the float normals itself"
+  31)
 
 
 (defn- check
@@ -90,7 +95,7 @@
                                         :padding 0 :radius 6378000.0}
                                        config-struct arena)]
             (check
-              (level- world config* 0 1 256
+              (level- world config* 0 1 256 all-but-normal-bytes
                       (fn [_ k b a day night water surface normals _normal-bytes]
                         (let [face  (index->face k)
                               image (fn [p] {:sfsim.image/width color-tilesize :sfsim.image/height color-tilesize

@@ -631,7 +631,7 @@ extern "C" int sfsim_cubemap_tiles_timed(void *world, const sfsim_cubemap_config
 // make-cube-map for this rank's share of a level (globe.clj:41-72), streamed: while the host callback consumes batch
 // i - 1 from page-locked memory, the copy engine brings batch i back and the SMs compute batch i + 1.
 extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg, int rank, int world_size, int batch_tiles,
-                                   sfsim_cubemap_tile_fn fn, void *user) {
+                                   int outputs, sfsim_cubemap_tile_fn fn, void *user) {
   World *w = (World *)world;
   if (ensure_init()) return 1;
   if (!w) return fail("world must not be NULL");
@@ -639,6 +639,7 @@ extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg,
   TileJob job;
   if (make_job(*w, cfg, job)) return 1;
   if (batch_tiles < 1 || batch_tiles > 65535) return fail("batch_tiles must be in [1, 65535]");
+  if (outputs <= 0 || outputs > SFSIM_CUBEMAP_ALL) return fail("outputs must be a non-empty mask of SFSIM_CUBEMAP_* bits");
   int count = 0;
   if (sfsim_cubemap_tile_shard(cfg->out_level, rank, world_size, 0, nullptr, &count)) return 1;
   std::vector<int> tiles((size_t)std::max(count, 1) * 3);
@@ -652,7 +653,7 @@ extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg,
     if (!set.computed) CUDA_TRY(cudaEventCreateWithFlags(&set.computed, cudaEventDisableTiming));
     if (!set.copied) CUDA_TRY(cudaEventCreateWithFlags(&set.copied, cudaEventDisableTiming));
     for (int k = 0; k < 6; k++)
-      if (set.host_bytes[k] < per_tile[k] * batch_tiles) {
+      if ((outputs >> k & 1) && set.host_bytes[k] < per_tile[k] * batch_tiles) {
         CUDA_TRY(cudaDeviceSynchronize());
         cudaFreeHost(set.host[k]);
         set.host[k] = nullptr;
@@ -661,7 +662,8 @@ extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg,
         set.host_bytes[k] = per_tile[k] * batch_tiles;
       }
   }
-  const bool want[6] = {true, true, true, true, true, true};
+  bool want[6];
+  for (int k = 0; k < 6; k++) want[k] = (outputs >> k & 1) != 0;
   const int nbatches = (count + batch_tiles - 1) / batch_tiles;
   auto batch_size = [&](int i) { return std::min(batch_tiles, count - i * batch_tiles); };
   auto deliver = [&](int i) -> int {       // hand the tiles of batch i to the host, in order
@@ -669,11 +671,10 @@ extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg,
     CUDA_TRY(cudaEventSynchronize(set.copied));
     for (int t = 0; t < batch_size(i); t++) {
       const int *tile = &tiles[(size_t)(i * batch_tiles + t) * 3];
-      if (fn(user, tile[0], tile[1], tile[2], (const unsigned char *)set.host[0] + per_tile[0] * t,
-             (const unsigned char *)set.host[1] + per_tile[1] * t, (const unsigned char *)set.host[2] + per_tile[2] * t,
-             (const float *)((const char *)set.host[3] + per_tile[3] * t),
-             (const float *)((const char *)set.host[4] + per_tile[4] * t),
-             (const signed char *)set.host[5] + per_tile[5] * t))
+      const char *p[6];
+      for (int k = 0; k < 6; k++) p[k] = want[k] ? (const char *)set.host[k] + per_tile[k] * t : nullptr;
+      if (fn(user, tile[0], tile[1], tile[2], (const unsigned char *)p[0], (const unsigned char *)p[1],
+             (const unsigned char *)p[2], (const float *)p[3], (const float *)p[4], (const signed char *)p[5]))
         return fail("the tile callback reported an error");
     }
     return 0;
@@ -687,7 +688,8 @@ extern "C" int sfsim_cubemap_level(void *world, const sfsim_cubemap_config *cfg,
     CUDA_TRY(cudaStreamWaitEvent(w->copy_stream, set.computed, 0));
     // the host image of this set was consumed by deliver(i - 2), which ran before this point
     for (int k = 0; k < 6; k++)
-      CUDA_TRY(cudaMemcpyAsync(set.host[k], set.dev[k], per_tile[k] * batch_size(i), cudaMemcpyDeviceToHost, w->copy_stream));
+      if (want[k])
+        CUDA_TRY(cudaMemcpyAsync(set.host[k], set.dev[k], per_tile[k] * batch_size(i), cudaMemcpyDeviceToHost, w->copy_stream));
     CUDA_TRY(cudaEventRecord(set.copied, w->copy_stream));
     if (i >= 1 && deliver(i - 1)) return 1;
   }
@@ -700,7 +702,8 @@ extern "C" int sfsim_cubemap_tile_counter(void *user, int, int, int, const unsig
   long long *acc = (long long *)user;
   if (!acc) return 1;
   acc[0] += 1;
-  acc[1] += day[0] + night[0] + water[0] + (surface[0] != 0.f) + (normals[0] != 0.f) + normal_bytes[0];
+  acc[1] += (day ? day[0] : 0) + (night ? night[0] : 0) + (water ? water[0] : 0) + (surface && surface[0] != 0.f) +
+            (normals && normals[0] != 0.f) + (normal_bytes ? normal_bytes[0] : 0);
   return 0;
 }
 

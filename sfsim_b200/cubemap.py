@@ -28,6 +28,16 @@ class CubemapConfig(C.Structure):
         return (1 << self.sublevel) * (self.surface_tilesize - 1) + 1
 
 
+ALL_OUTPUTS = ("day", "night", "water", "surface", "normals", "normal_bytes")     # bit k of the C mask = entry k
+
+
+def _mask(outputs):
+    unknown = set(outputs) - set(ALL_OUTPUTS)
+    if unknown:
+        raise TypeError("unknown outputs %s" % sorted(unknown))
+    return sum(1 << ALL_OUTPUTS.index(name) for name in set(outputs))
+
+
 TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_void_p)
 
@@ -301,22 +311,25 @@ class World:
         check(_lib.load().sfsim_cubemap_tiles_timed(self._h, C.byref(cfg), len(tiles), _lib.ptr(tiles), C.byref(ms)))
         return ms.value
 
-    def time_cube_map_level(self, cfg, rank=0, world_size=1, batch=256):
+    def time_cube_map_level(self, cfg, rank=0, world_size=1, batch=256, outputs=ALL_OUTPUTS):
         """seconds for sfsim_cubemap_level with the library's counting callback (no consumer): (seconds, tiles)"""
         import time
         acc = (C.c_longlong * 2)(0, 0)
         lib = _lib.load()
         fn = C.cast(lib.sfsim_cubemap_tile_counter, TILE_FN)
         t0 = time.perf_counter()
-        check(lib.sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch), fn, C.byref(acc)))
+        check(lib.sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch), _mask(outputs), fn,
+                                      C.byref(acc)))
         return time.perf_counter() - t0, int(acc[0])
 
-    def make_cube_map(self, in_level, out_level, on_tile, rank=0, world_size=1, batch=256, **kw):
+    def make_cube_map(self, in_level, out_level, on_tile, rank=0, world_size=1, batch=256, outputs=ALL_OUTPUTS, **kw):
         """make-cube-map (globe.clj:29-80) for this rank's tiles of the output level, streamed: `on_tile((face, b, a),
         tile)` is called for every tile with a dict of array views (day, night, water, surface, normals, normal_bytes)
         into page-locked memory that is valid during the call only -- the place to encode and write the tile's five files
         (spit-jpg, spit-bytes-gz, spit-floats-gz, spit-normals).  While the callback works on one batch the next one
-        crosses PCIe and the one after is being computed.  Returns the number of tiles delivered."""
+        crosses PCIe and the one after is being computed.  `outputs`: the arrays to compute and bring back (the bus is
+        the bound; leave "normals" out if `normal_bytes` is all the PNG encoder needs).  Returns the number of tiles
+        delivered."""
         cfg = make_config(in_level, out_level, width=self.width, **kw)
         st, ct = cfg.surface_tilesize, cfg.color_tilesize
         pitch = (ct + 3) & ~3
@@ -328,7 +341,7 @@ class World:
         def trampoline(_user, face, b, a, *ptrs):
             try:
                 tile = {name: np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
-                        for (name, ctype, shape), p in zip(shapes, ptrs)}
+                        for (name, ctype, shape), p in zip(shapes, ptrs) if p}
                 on_tile((face, b, a), tile)
                 delivered[0] += 1
                 return 0
@@ -337,7 +350,8 @@ class World:
                 return 1
 
         fn = TILE_FN(trampoline)
-        status = _lib.load().sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch), fn, None)
+        status = _lib.load().sfsim_cubemap_level(self._h, C.byref(cfg), int(rank), int(world_size), int(batch),
+                                                 _mask(outputs), fn, None)
         if failure:
             raise failure[0]
         check(status)

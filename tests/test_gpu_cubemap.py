@@ -232,6 +232,22 @@ def test_the_streamed_level_delivers_every_tile_once_and_equals_the_batch_call()
         assert gw.make_cube_map(0, 2, on_tile, rank=rank, world_size=world_size, batch=batch, surface_tilesize=17) == len(tiles)
         assert len(seen) == len(tiles)
 
+    # a subset of the arrays: the others are neither brought back nor handed over; encoded normals without float normals
+    tiles = cubemap.tile_shard(2)
+    want = gw.make_cube_map_tiles(cfg, tiles)
+    got = []
+
+    def subset(key, tile):
+        assert sorted(tile) == ["normal_bytes", "water"]
+        n = len(got)
+        assert tile["water"].tobytes() == want["water"][n].tobytes()
+        assert tile["normal_bytes"].tobytes() == want["normal_bytes"][n].tobytes()
+        got.append(key)
+
+    assert gw.make_cube_map(0, 2, subset, batch=50, outputs=("water", "normal_bytes"), surface_tilesize=17) == len(tiles)
+    with pytest.raises(TypeError):
+        gw.make_cube_map(0, 2, subset, outputs=("water", "colour"), surface_tilesize=17)
+
     class Stop(Exception):
         pass
 
