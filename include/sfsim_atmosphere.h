@@ -222,6 +222,11 @@ int atmlut_index_backward_batch(const atmlut_planet *planet, int which, const in
 int atmlut_index_map_batch(const atmlut_planet *planet, int fn, int size, int count, const double *a,
                            const double *b, const int *flag, double *out, int *out_flag);
 
+/* scattering (fn 0, atmosphere.clj:42-47), extinction (fn 1, :50-53): arg = heights, out = double[count][3];
+ * phase (fn 2, :56-61): arg = cosines of the scattering angle, out[3 i] = value.  The device functions every table
+ * kernel inlines, evaluated at arbitrary arguments. */
+int atmlut_medium_batch(const atmlut_scatter *component, int fn, int count, const double *arg, double *out);
+
 /* interpolate-value (interpolate.clj:87-98) on a float table of `ncomp`-vectors, dims <= 4 */
 int atmlut_interpolate_batch(const float *table, const int *shape, int dims, int ncomp, int count,
                              const double *coords, float *out);

@@ -71,7 +71,7 @@ EXPORTS = [
     "atmlut_point_scatter_first_order_batch", "atmlut_ray_scatter_first_order_batch",
     "atmlut_ray_scatter_table_batch", "atmlut_point_scatter_batch", "atmlut_surface_radiance_batch",
     "atmlut_index_forward_batch", "atmlut_index_backward_batch", "atmlut_index_map_batch",
-    "atmlut_interpolate_batch",
+    "atmlut_interpolate_batch", "atmlut_medium_batch",
     "atmlut_convert_4d_to_2d", "atmlut_write_floats", "atmlut_read_floats",
     # include/sfsim_noise.h
     "sfsim_worley_noise", "sfsim_perlin_noise", "sfsim_worley_distances", "sfsim_perlin_samples",

@@ -45,6 +45,19 @@ def phase(component, mu):
     return (3.0 * (1.0 - g2) * (1.0 + mu * mu)) / (8.0 * math.pi * (2.0 + g2) * math.pow((1.0 + g2) - 2.0 * g * mu, 1.5))
 
 
+def medium_batch(component, fn, args):
+    """scattering (fn 0), extinction (fn 1) of `component` at heights `args`, or its phase function (fn 2) at cosines
+    `args`, evaluated by the device functions the table kernels inline (atmlut_medium_batch): array [n][3] (fn 0, 1)
+    or [n] (fn 2).  The functions above are the host-side mirror of the same formulas."""
+    import ctypes as C
+    from . import _lib
+    a = _lib.f64(args).reshape(-1)
+    out = np.zeros((len(a), 3))
+    sc = _lib.make_scatter(component)
+    _lib.check(_lib.load().atmlut_medium_batch(C.byref(sc), int(fn), len(a), _lib.ptr(a), _lib.ptr(out)))
+    return out[:, 0] if fn == 2 else out
+
+
 def height(planet, point):
     """sphere.clj:28-31"""
     d = np.asarray(point, dtype=np.float64) - np.asarray(planet.get("centre", (0, 0, 0)), dtype=np.float64)

@@ -433,6 +433,22 @@ std::vector<Ring> make_rings(int theta_steps, int phi_steps, double theta_range,
   return rings;
 }
 
+// atmosphere.clj:42-61 at arbitrary arguments: fn 0 scattering (height -> rgb), 1 extinction (height -> rgb),
+// 2 phase (mu -> value, stored in out[3 i])
+__global__ void k_medium_batch(Medium m, int fn, int count, const double *__restrict__ arg, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (fn == 2) {
+    out[3 * i] = phase(m.g[0], arg[i]);
+    out[3 * i + 1] = out[3 * i + 2] = 0.0;
+    return;
+  }
+  for (int ch = 0; ch < 3; ch++) {
+    const double sc = scattering(m, 0, ch, arg[i]);
+    out[3 * i + ch] = fn == 0 ? sc : sc / m.quotient[0];
+  }
+}
+
 struct Bufs {
   std::vector<void *> ptrs;
   ~Bufs() {
@@ -759,6 +775,20 @@ extern "C" int atmlut_index_map_batch(const atmlut_planet *planet, int fn, int s
       for (int k = 0; k < 3; k++) out[3 * i + k] += planet->centre[k];
   if (out_flag && bufs.down(doflag, (size_t)count, out_flag)) return 1;
   return 0;
+}
+
+extern "C" int atmlut_medium_batch(const atmlut_scatter *component, int fn, int count, const double *arg, double *out) {
+  atmlut_planet unit = {{0, 0, 0}, 1.0, 1.0, {0, 0, 0}};
+  Params P;
+  if (ensure_init() || make_planet_medium(&unit, component, component ? 1 : 0, P)) return 1;
+  CHECK_ARGS(component && fn >= 0 && fn <= 2 && count >= 0 && arg && out, "invalid argument");
+  if (count == 0) return 0;
+  Bufs bufs;
+  double *da, *dout;
+  if (bufs.up(arg, (size_t)count, da) || bufs.up<double>(nullptr, (size_t)count * 3, dout)) return 1;
+  k_medium_batch<<<blocks(count, 64), 64, 0, stream()>>>(P.medium, fn, count, da, dout);
+  CUDA_TRY(cudaGetLastError());
+  return bufs.down(dout, (size_t)count * 3, out);
 }
 
 extern "C" int atmlut_interpolate_batch(const float *table, const int *shape, int dims, int ncomp, int count,

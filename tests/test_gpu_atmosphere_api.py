@@ -42,6 +42,26 @@ def test_scattering_extinction_phase():
     assert atm.phase({"g": 0.5}, 1.0) == pytest.approx((6 * 0.75) / (8 * PI * 2.25 * 0.25 ** 1.5))
 
 
+def test_scattering_extinction_phase_on_the_device():
+    """the same facts (t_atmosphere.clj:72-100) through the device functions the table kernels inline, and the device
+    against the host mirror at random arguments"""
+    r = {"base": (5.8e-6,) * 3, "scale": 8000.0}
+    sc = atm.medium_batch(r, 0, [0.0, 8000.0, 16000.0])
+    assert sc[0, 0] == 5.8e-6
+    assert sc[1, 0] == roughly(5.8e-6 / E, 1e-12) and sc[2, 0] == roughly(5.8e-6 / E / E, 1e-12)
+    m = {"base": (2e-5,) * 3, "scale": 1200.0, "quotient": 0.9}
+    assert atm.medium_batch(m, 1, [1200.0])[0, 0] == roughly(2e-5 / 0.9 / E, 1e-12)
+    assert atm.medium_batch({"base": (1, 1, 1), "scale": 1.0}, 2, [0.0, 1.0]).tolist() == pytest.approx([3 / (16 * PI), 6 / (16 * PI)])
+    half = {"base": (1, 1, 1), "scale": 1.0, "g": 0.5}
+    assert atm.medium_batch(half, 2, [0.0, 1.0]).tolist() == pytest.approx(
+        [(3 * 0.75) / (8 * PI * 2.25 * 1.25 ** 1.5), (6 * 0.75) / (8 * PI * 2.25 * 0.25 ** 1.5)])
+    rng = np.random.default_rng(3)
+    hs, mus = rng.uniform(0, 1e5, 200), rng.uniform(-1, 1, 200)
+    np.testing.assert_allclose(atm.medium_batch(mie, 0, hs), [atm.scattering(mie, h) for h in hs], rtol=1e-14)
+    np.testing.assert_allclose(atm.medium_batch(mie, 1, hs), [atm.extinction(mie, h) for h in hs], rtol=1e-14)
+    np.testing.assert_allclose(atm.medium_batch(mie, 2, mus), [atm.phase(mie, mu) for mu in mus], rtol=1e-13)
+
+
 # t_atmosphere.clj:144-172
 def test_transmittance_known_answers():
     r = {"base": (5.8e-6, 13.5e-6, 33.1e-6), "scale": 8000.0}
