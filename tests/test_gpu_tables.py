@@ -443,3 +443,30 @@ def test_the_builder_reports_the_sampler_it_picked():
         b.sync()
         assert b.work()["mufu_ex2_per_esample"] == want
         b.close()
+
+
+def test_generate_into_page_locked_and_pageable_buffers_gives_the_same_bytes():
+    """atmlut_generate makes the four downloads nodes of the build graph when the destinations are page-locked and
+    re-captures the graph when they change; pageable destinations go through the library's staging buffers.  Every
+    variant, in any order, must deliver the same bytes."""
+    cfg = lib_config(REDUCED, iterations=2)
+    want = [t.copy() for t in atmosphere_lut.generate_tables(cfg=cfg)]                    # pageable
+    pinned_a = atmosphere_lut.allocate_outputs(cfg, pinned=True)
+    pinned_b = atmosphere_lut.allocate_outputs(cfg, pinned=True)
+    lib = _lib.load()
+    nbytes = [t.nbytes for t in want]
+    owned = [lib.atmlut_host_alloc(n) for n in nbytes]                                    # the library's own allocator
+    assert all(owned)
+    owned_views = [np.frombuffer((C.c_char * n).from_address(p), dtype=np.float32).reshape(t.shape)
+                   for p, n, t in zip(owned, nbytes, want)]
+    try:
+        for out in (pinned_a, pinned_b, pinned_a, None, owned_views, pinned_b, None):
+            if out is not None:
+                for t in out:
+                    t.fill(-1.0)
+            got = atmosphere_lut.generate_tables(cfg=cfg, out=out)
+            for g, w in zip(got, want):
+                assert g.tobytes() == w.tobytes()
+    finally:
+        for p in owned:
+            lib.atmlut_host_free(C.c_void_p(p))
