@@ -547,19 +547,23 @@ def run_b200(args):
                                              "densities from one exponential as t^20 and t^3 on the FMA pipe): "
                                              "`mufu_pipe_frac` is the MUFU pipe's own utilisation by these exponentials",
                         "esamples_per_launch": work["esamples_first_order"], "launch_ms": first_ms}
-        # ray-scatter from the dJ table: bound by shared-memory wavefronts.  Floor per 4-D lookup of one warp:
-        # 4 x LDS.128 (16 wavefronts) for the bilinear corners + 1 x STS.128 (4) for its share of the blended tile.
+        # ray-scatter from the dJ table: bound by shared-memory wavefronts.  Algorithmic bytes per 4-D lookup: four
+        # RGB corners of the blended tile (48 B read) and the thread's share of the tile (12 B written) = 60 B, i.e. 15
+        # wavefronts of 128 B per warp-lookup (the kernel keeps red/green and blue in separate planes, so no padding
+        # lane is moved; with padded float4 texels -- the model of round 1 -- it would be 20).
         roofline_k6 = None
         if ray_ms and cfg.iterations:
             lookups = (n4 / world) * 100.0 * cfg.iterations
             per_s = lookups / (ray_ms * 1e-3)
-            peak = sm_count * clock_hz * 32.0 / 20.0
+            peak = sm_count * clock_hz * 32.0 / 15.0
             roofline_k6 = {"bound": "shared-memory wavefronts", "kernel": "k_ray_scatter", "achieved": per_s / 1e9,
                            "peak": peak / 1e9, "unit": "G lookups/s", "frac": per_s / peak,
-                           "model": "1 wavefront / clk / SM; 20 wavefronts per warp-lookup (4 LDS.128 + 1 STS.128), "
-                                    "%d SMs at the measured %.0f MHz" % (sm_count, clock_hz / 1e6),
+                           "frac_padded_float4_model": per_s / (sm_count * clock_hz * 32.0 / 20.0),
+                           "model": "1 wavefront (128 B) / clk / SM; 60 algorithmic bytes per lookup = 15 wavefronts per "
+                                    "warp-lookup, %d SMs at the measured %.0f MHz" % (sm_count, clock_hz / 1e6),
                            "lookups_per_pass": lookups / cfg.iterations, "pass_ms": ray_ms / cfg.iterations,
-                           "measured_counters": "profiles/ (ncu): shared wavefronts and thread-instructions per lookup"}
+                           "measured_counters": "profiles/r2/r2_final_ncu_summary.txt: 28.5 shared wavefronts and 121 "
+                                                "thread-instructions per warp-lookup"}
         line = {"metric": METRIC, "value": texels / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3) + 2, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
