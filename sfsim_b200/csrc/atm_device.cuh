@@ -164,10 +164,12 @@ __device__ __forceinline__ void density_sums_fast(const Fast &f, bool swap, cons
   // e_i(m) = u(m+i) - u(m) = i d1(m) + (i (i-1) / 2) d2, which grow by 4 i d2 per trip
   double step4 = 4.0 * d1 + 6.0 * d2;              // u(m+4) - u(m)
   const double step4_inc = 16.0 * d2;
-  float e1 = (float)d1;
-  float2 e23 = make_float2((float)(2.0 * d1 + d2), (float)(3.0 * d1 + 3.0 * d2));
-  const float e1_inc = (float)(4.0 * d2);
-  const float2 e23_inc = make_float2((float)(8.0 * d2), (float)(12.0 * d2));
+  // the float differences from two conversions (they share the MUFU pipe): multiples of d2 by powers of two are exact
+  const float d1f = (float)d1, d2f = (float)d2;
+  float e1 = d1f;
+  float2 e23 = make_float2(fmaf(2.0f, d1f, d2f), fmaf(3.0f, d1f, 3.0f * d2f));
+  const float e1_inc = 4.0f * d2f;
+  const float2 e23_inc = make_float2(8.0f * d2f, 12.0f * d2f);
   float2 acc0a = make_float2(0.f, 0.f), acc1a = make_float2(0.f, 0.f);
   float2 acc0b = make_float2(0.f, 0.f), acc1b = make_float2(0.f, 0.f);
   int j = 0;

@@ -74,6 +74,7 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
   const double ll = dot(l, l);
   const double llen = sqrt(ll);
   const double inv_ll = 1.0 / ll;   // the end point of the sun ray only places samples; an ulp there is harmless
+  const double quad_b = (2.0 * inv_steps) * P.fast.inv_rp2, quad_c = ((ll * inv_steps) * inv_steps) * P.fast.inv_rp2;
   for (int k = k0; k < k1; k += kstride) {
     const double pkx = vs.pkx[k], pky = vs.pky[k], rk2 = vs.rk2[k];
     const double pl = l.x * pkx + l.y * pky;
@@ -90,7 +91,11 @@ __device__ __forceinline__ void first_order_texel(const Params &P, const ViewSme
       t = fmax(0.0, middle);
     }
     // transmittance p_k -> end point: samples p_k + (l t)(j + 1/2)/steps
-    Quad q = make_quad(P.fast, rk2, pl * t, ll * t * t, steps);
+    // make_quad(P.fast, rk2, pl t, ll t^2, steps) with the factors that do not depend on k worked out once per texel
+    Quad q;
+    q.A = (rk2 - P.fast.rp2) * P.fast.inv_rp2;
+    q.B = quad_b * (pl * t);
+    q.C = quad_c * (t * t);
     float s0, s1;
     density_sums_seq(P, q, steps, s0, s1);
     esamples += steps;

@@ -96,7 +96,8 @@ def column_shipped_model(r0, mu, t_end, mufu_noise=0.0, rng=None):
     base = (4 * (j // 4) + 0.5)[None, :]                                   # m of the group's first sample
     i = (j % 4)[None, :].astype(np.float64)
     u_base = trunc_to_f32(a + base * (b + base * c))                       # float64 chain, truncated
-    diff = (i * b + c * (2.0 * base * i + i * i)).astype(f32)              # u(m + i) - u(m), kept in float32
+    diff = (i * b + c * (2.0 * base * i + i * i)).astype(f32)              # u(m + i) - u(m), kept in float32 (the device
+    #                                                                       advances them by float additions per group)
     uf = (u_base + diff).astype(f32)
     q = fma32(uf, np.full_like(uf, f32(0.0625)), np.full_like(uf, f32(-0.125)))
     q = fma32(q, uf, np.full_like(uf, f32(0.5)))
