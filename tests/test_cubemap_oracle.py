@@ -257,3 +257,27 @@ def test_tile_against_the_pointwise_functions():
     # neighbouring tiles share their border pixels (the pixel grid includes both tile edges)
     t2 = w.make_cube_map_tile(face, in_level, out_level, b, a + 1, surface_tilesize=st)
     assert (t["day"][:, -1] == t2["day"][:, 0]).all()
+
+
+def test_oracle_reproduces_the_committed_golden_tiles():
+    """tests/golden/cubemap_tiles.npz (tests/golden/make_cubemap_golden.py): the oracle of this checkout must still
+    produce the committed tiles -- integer arrays exactly, float arrays to the last bit on the machine that made them
+    and within one float32 ulp elsewhere (another libm may differ in the last double bit of atan2 / sin / cos)."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_cubemap_golden", os.path.join(here, "make_cubemap_golden.py"))
+    gold_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gold_mod)
+    gold = np.load(os.path.join(here, "cubemap_tiles.npz"))
+    elev, day, night = gold_mod.world()
+    ow = cm.OracleWorld(gold_mod.WIDTH, elev, day, night)
+    for n, t in enumerate(gold_mod.TILES):
+        tile = ow.make_cube_map_tile(t["face"], t["in_level"], t["out_level"], t["b"], t["a"],
+                                     surface_tilesize=gold_mod.SURFACE_TILESIZE)
+        for k in ("day", "night", "water"):
+            diff = tile[k].astype(np.int32) - gold["%d_%s" % (n, k)].astype(np.int32)
+            assert np.abs(diff).max() <= 1 and (diff != 0).mean() < 1e-3, (n, k)
+        for k in ("surface", "normals"):
+            want = gold["%d_%s" % (n, k)]
+            assert np.abs(tile[k].astype(np.float64) - want).max() <= float(np.spacing(np.abs(want).max())), (n, k)

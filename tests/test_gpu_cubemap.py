@@ -258,3 +258,27 @@ def test_the_streamed_level_delivers_every_tile_once_and_equals_the_batch_call()
         gw.make_cube_map(0, 2, failing, batch=4, surface_tilesize=17)
     assert gw.make_cube_map(0, 0, lambda key, tile: None, rank=7, world_size=8, surface_tilesize=17) == 0
     gw.close()
+
+
+def test_committed_golden_tiles():
+    """the GPU against tests/golden/cubemap_tiles.npz (made by the oracle, tests/golden/make_cubemap_golden.py)"""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_cubemap_golden", os.path.join(here, "make_cubemap_golden.py"))
+    gold_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gold_mod)
+    gold = np.load(os.path.join(here, "cubemap_tiles.npz"))
+    elev, day, night = gold_mod.world()
+    gw = cubemap.World(gold_mod.WIDTH)
+    for level, a in elev.items():
+        gw.set_elevation(level, a)
+    for level, a in day.items():
+        gw.set_color(False, level, a)
+        gw.set_color(True, level, night[level])
+    for n, t in enumerate(gold_mod.TILES):
+        cfg = cubemap.make_config(t["in_level"], t["out_level"], width=gold_mod.WIDTH, surface_tilesize=gold_mod.SURFACE_TILESIZE)
+        got = gw.make_cube_map_tiles(cfg, [(t["face"], t["b"], t["a"])])
+        want = {k: gold["%d_%s" % (n, k)] for k in ("day", "night", "water", "surface", "normals", "raw")}
+        assert_tile_equal({k: v[0] for k, v in got.items()}, want, ("golden", n))
+    gw.close()
