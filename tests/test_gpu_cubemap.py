@@ -282,3 +282,39 @@ def test_committed_golden_tiles():
         want = {k: gold["%d_%s" % (n, k)] for k in ("day", "night", "water", "surface", "normals", "raw")}
         assert_tile_equal({k: v[0] for k, v in got.items()}, want, ("golden", n))
     gw.close()
+
+
+def test_make_cube_map_writes_the_files_of_a_level(tmp_path):
+    """sfsim_b200.globe.make_cube_map (globe.clj:29-96): every tile of a level as the five files of the reference's layout,
+    read back against the arrays of the batch call; then the tar step"""
+    import os
+    import tarfile
+    from PIL import Image
+    from sfsim_b200 import globe
+    width = 16
+    elev, day, night = ocm.synthetic_world(width, [0, 1], [1], seed=19)
+    gw = cubemap.World(width)
+    for level in (0, 1):
+        gw.set_elevation(level, elev[level])
+    gw.set_color(False, 1, day[1])
+    gw.set_color(True, 1, night[1])
+    prefix = str(tmp_path / "globe")
+    assert globe.make_cube_map(gw, 0, 1, prefix=prefix, batch=7, surface_tilesize=9) == 24
+    tiles = cubemap.tile_shard(1)
+    want = gw.make_cube_map_tiles(cubemap.make_config(0, 1, width=width, surface_tilesize=9), tiles)
+    for n, (face, b, a) in enumerate(tiles.tolist()):
+        path = lambda suffix: globe.cube_path(prefix, face, 1, b, a, suffix)
+        assert globe.slurp_bytes_gz(path(".water.gz")).tobytes() == want["water"][n].tobytes()
+        assert globe.slurp_floats_gz(path(".surf.gz")).tobytes() == want["surface"][n].tobytes()
+        assert np.asarray(Image.open(path(".png"))).view(np.int8).tobytes() == want["normal_bytes"][n].tobytes()
+        assert np.abs(globe.slurp_normals(path(".png")) - want["normals"][n]).max() <= 0.5 / 127.5 + 1e-6
+        jpg = np.asarray(Image.open(path(".jpg")).convert("RGB")).astype(np.int32)
+        assert jpg.shape == (17, 17, 3)                       # lossy: only the size and a loose resemblance
+        assert Image.open(path(".night.jpg")).size == (17, 17)
+    globe.make_cube_map_tars(1, prefix)
+    for face in range(6):
+        for a in range(2):
+            with tarfile.open(globe.cube_tar(prefix, face, 1, a)) as tar:
+                assert len(tar.getnames()) == 2 * 5           # two rows b, five files each
+            assert not os.path.exists(globe.cube_dir(prefix, face, 1, a))
+    gw.close()
