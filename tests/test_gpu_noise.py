@@ -2,6 +2,8 @@
 
 Integer-free but deterministic arithmetic (+, -, *, /, sqrt, floor in IEEE double, no fused multiply-add): the
 un-normalised samples must equal the oracle's BIT FOR BIT, the float32 textures likewise."""
+import os
+
 import numpy as np
 import pytest
 
@@ -110,3 +112,17 @@ def test_blue_noise_texture_of_the_build_task():
     np.testing.assert_array_equal(tex, want.astype(np.float32))
     spectrum = np.abs(np.fft.fft2(tex.reshape(m, m) - tex.mean())) ** 2
     assert spectrum[:4, :4].sum() - spectrum[0, 0] < 0.01 * spectrum.sum()      # low frequencies are suppressed
+
+
+def test_build_tasks_write_the_files_of_build_clj(tmp_path):
+    """sfsim_b200.build mirrors build.clj:34-51,84-87: file names, sizes and value ranges of the noise textures"""
+    from sfsim_b200 import build
+    clouds, data = str(tmp_path / "clouds"), str(tmp_path)
+    build.worley(size=8, divisions=2, out_dir=clouds)
+    build.perlin(size=8, divisions=2, out_dir=clouds)
+    build.bluenoise(size=16, out_dir=data)
+    for name in ("worley-north.raw", "worley-south.raw", "worley-cover.raw", "perlin.raw"):
+        a = np.fromfile(os.path.join(clouds, name), dtype="<f4")
+        assert a.size == 8 ** 3 and a.min() >= 0.0 and a.max() <= 1.0 and a.max() - a.min() > 0.5
+    b = np.fromfile(os.path.join(data, "bluenoise.raw"), dtype="<f4")
+    assert sorted(np.rint(b * 256).astype(int).tolist()) == list(range(256))        # every rank once, scaled by 1 / size^2
