@@ -263,12 +263,12 @@ def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
     resident in device memory.  Tiles are independent: rank r takes every world-th tile, no exchange (weak scaling is
     the natural mode; here the level is a fixed job, so this is strong scaling of the 1536-tile level)."""
     import numpy as np
-    from oracle import cubemap as ocm                 # synthetic rasters and the CPU baseline only
     from sfsim_b200 import cubemap
+    from sfsim_b200.synthetic import synthetic_world
     in_level = out_level - 3                           # build.clj:300-310
     cfg = cubemap.make_config(in_level, out_level)
     ls, lc, lw = max(0, min(4, in_level)), max(0, min(5, in_level + 1)), max(0, min(4, in_level + 1))
-    elev, day, night = ocm.synthetic_world(675, sorted({ls, lw}), [lc], seed=1)
+    elev, day, night = synthetic_world(675, sorted({ls, lw}), [lc], seed=1)
     w = cubemap.World(675)
     for level, a in elev.items():
         w.set_elevation(level, a)
@@ -319,6 +319,7 @@ def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
                                              "d2h_bytes_per_level_this_rank": (per_tile - cfg.color_tilesize ** 2 * 12) * len(tiles)}},
            "bound": "FP64 pipe / issue slots (ncu: profiles/r2/); DRAM traffic 1.2 GB per level = the outputs"}
     if with_cpu and rank == 0:
+        from oracle import cubemap as ocm             # the cpu_baseline leg: the C restatement on the host cores
         ow = ocm.OracleWorld(675, elev, day, night)
         sample = [tuple(t) for t in tiles[:: max(1, len(tiles) // 4)][:4]]
         t0 = time.perf_counter()

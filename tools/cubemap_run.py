@@ -8,7 +8,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-from oracle import cubemap as ocm  # noqa: E402  (synthetic rasters only)
+from sfsim_b200 import synthetic as ocm  # noqa: E402
 from sfsim_b200 import cubemap  # noqa: E402
 
 out_level = int(sys.argv[1]) if len(sys.argv) > 1 else 4

@@ -36,7 +36,7 @@ if "batch" in which:
     print(atmosphere.point_scatter(earth, sc, tab, e, (1, 1, 1), 6, 8, (6379000.0, 0, 0), (0, 1, 0), (0.6, 0.8, 0)))
     print(atmosphere.surface_radiance(earth, tab, 8, (6379000.0, 0, 0), (0.6, 0.8, 0)))
 if "cubemap" in which:
-    from oracle import cubemap as ocm                   # synthetic rasters only
+    from sfsim_b200 import synthetic as ocm
     from sfsim_b200 import cubemap
     width = 16
     elev, day, night = ocm.synthetic_world(width, [0, 1], [1], seed=3)
