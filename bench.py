@@ -321,7 +321,8 @@ def cubemap_bench(rank, world, runner, with_cpu, out_level=4):
     if with_cpu and rank == 0:
         from oracle import cubemap as ocm             # the cpu_baseline leg: the C restatement on the host cores
         ow = ocm.OracleWorld(675, elev, day, night)
-        sample = [tuple(t) for t in tiles[:: max(1, len(tiles) // 4)][:4]]
+        sample = [tuple(t) for t in tiles[:: max(1, len(tiles) // 32)][:32]]
+        ow.make_cube_map_tile(*sample[0][:1], in_level, out_level, *sample[0][1:])      # warm-up: threads, page faults
         t0 = time.perf_counter()
         for face, b, a in sample:
             ow.make_cube_map_tile(face, in_level, out_level, b, a)
